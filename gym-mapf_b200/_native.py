@@ -1,0 +1,299 @@
+"""ctypes binding of the C ABI in include/mapf_b200.h (csrc/libmapf_b200.so).
+
+The hot path has no CPU fallback: a missing library, a missing CUDA device or a failing call raises."""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(CSRC, "libmapf_b200.so")
+
+MAPF_OK, MAPF_ERR_INVALID, MAPF_ERR_KEY, MAPF_ERR_UNSUPPORTED, MAPF_ERR_CUDA, MAPF_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+MAPF_SOC, MAPF_MAKESPAN = 0, 1
+OPT_AUTO_RESET = 1
+FLAG_DONE, FLAG_COLLISION = 1, 2
+
+EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
+           "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_expand",
+           "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_rollout", "mapf_step_host",
+           "mapf_last_error", "mapf_version"]
+
+
+class MapfSpec(C.Structure):
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("obstacles", C.c_void_p), ("n_agents", C.c_int32),
+                ("start_rc", C.c_void_p), ("goal_rc", C.c_void_p), ("fail_prob", C.c_double),
+                ("reward_of_clash", C.c_double), ("reward_of_goal", C.c_double), ("reward_of_living", C.c_double),
+                ("criterion", C.c_int32)]
+
+
+class MapfInfo(C.Structure):
+    _fields_ = [("n_agents", C.c_int32), ("n_cells", C.c_int32), ("state_words", C.c_int32),
+                ("moves_in_smem", C.c_int32), ("n_actions", C.c_int64), ("n_states", C.c_uint64 * 2),
+                ("start_state", C.c_uint64 * 2), ("goal_state", C.c_uint64 * 2), ("max_row_len", C.c_int64),
+                ("device", C.c_int32), ("sm_count", C.c_int32)]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("mapf_b200 error %d: %s" % (code, text))
+        self.code = code
+        self.text = text
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    if verbose or out.returncode:
+        print(out.stdout + out.stderr)
+    if out.returncode:
+        raise RuntimeError("building libmapf_b200.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built: there is no fallback path."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `make -C %s` (or `python -c 'import __graft_entry__ as g; "
+                               "g.build()'`); gym_mapf_b200 has no CPU fallback" % (LIB_PATH, CSRC))
+        L = C.CDLL(LIB_PATH)
+        vp, i64, u64, u32, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int32
+        L.mapf_ctx_create.argtypes = [C.POINTER(MapfSpec), i32, C.POINTER(vp)]
+        L.mapf_ctx_destroy.argtypes = [vp]
+        L.mapf_ctx_destroy.restype = None
+        L.mapf_ctx_info.argtypes = [vp, C.POINTER(MapfInfo)]
+        L.mapf_ctx_moves.argtypes = [vp, vp, vp, vp, vp]
+        L.mapf_decode_states.argtypes = [vp, vp, i64, vp, vp]
+        L.mapf_encode_states.argtypes = [vp, vp, i64, vp, vp]
+        L.mapf_count_rows.argtypes = [vp, vp, vp, i64, vp, vp]
+        L.mapf_scan_scratch_bytes.argtypes = [i64]
+        L.mapf_scan_scratch_bytes.restype = i64
+        L.mapf_scan_rows.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mapf_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+        L.mapf_count_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, vp]
+        L.mapf_expand_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, vp, vp, vp, vp, vp]
+        L.mapf_checksum.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
+        L.mapf_step.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
+        L.mapf_rollout.argtypes = [vp, vp, vp, i64, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
+        L.mapf_step_host.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp]
+        L.mapf_last_error.restype = C.c_char_p
+        L.mapf_version.restype = C.c_char_p
+        _lib = L
+        return _lib
+
+
+def check(rc):
+    if rc != MAPF_OK:
+        text = lib().mapf_last_error().decode("utf8", "replace")
+        if rc == MAPF_ERR_KEY:
+            raise KeyError(text)  # the reference's KeyError for a start/goal on an obstacle (mapf_env.py:369)
+        raise NativeError(rc, text)
+
+
+def _ptr(t):
+    """Device (or host) address of a torch tensor / numpy array; None -> NULL."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Engine:
+    """One immutable device context (mapf_ctx) for one env spec on one CUDA device."""
+
+    def __init__(self, obstacles, n_agents, starts, goals, fail_prob, r_clash, r_goal, r_living, makespan, device=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_mapf_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback")
+        obstacles = np.ascontiguousarray(obstacles, dtype=np.uint8)
+        start_rc = np.ascontiguousarray(np.array(starts, dtype=np.int32).reshape(-1))
+        goal_rc = np.ascontiguousarray(np.array(goals, dtype=np.int32).reshape(-1))
+        spec = MapfSpec(obstacles.shape[0], obstacles.shape[1], obstacles.ctypes.data, int(n_agents),
+                        start_rc.ctypes.data, goal_rc.ctypes.data, float(fail_prob), float(r_clash), float(r_goal),
+                        float(r_living), MAPF_MAKESPAN if makespan else MAPF_SOC)
+        self.device_index = torch.device(device).index if not isinstance(device, int) else device
+        if self.device_index is None:
+            self.device_index = torch.cuda.current_device()
+        self.torch_device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        check(lib().mapf_ctx_create(C.byref(spec), self.device_index, C.byref(h)))
+        self._h = h
+        info = MapfInfo()
+        check(lib().mapf_ctx_info(self._h, C.byref(info)))
+        self.n = info.n_agents
+        self.L = info.n_cells
+        self.words = info.state_words
+        self.moves_in_smem = bool(info.moves_in_smem)
+        self.nA = info.n_actions
+        self.nS = info.n_states[0] | (info.n_states[1] << 64)
+        self.s0 = info.start_state[0] | (info.start_state[1] << 64)
+        self.goal_state = info.goal_state[0] | (info.goal_state[1] << 64)
+        self.max_row_len = info.max_row_len
+        self.sm_count = info.sm_count
+        self._moves = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mapf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # ---- helpers
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.torch_device).cuda_stream
+
+    def state_shape(self, B):
+        return (B,) if self.words == 1 else (B, 2)
+
+    def new_states(self, B):
+        import torch
+        return torch.empty(self.state_shape(B), dtype=torch.int64, device=self.torch_device)
+
+    def states_from_ints(self, values):
+        """Python ints -> state tensor on the device."""
+        import torch
+        m = (1 << 64) - 1
+        if self.words == 1:
+            arr = np.array([int(v) for v in values], dtype=np.uint64).view(np.int64)
+        else:
+            arr = np.array([[int(v) & m, (int(v) >> 64) & m] for v in values], dtype=np.uint64).view(np.int64)
+            arr = arr.reshape(-1, 2)
+        return torch.from_numpy(arr).to(self.torch_device)
+
+    def states_to_ints(self, t):
+        arr = t.detach().cpu().numpy().view(np.uint64)
+        if self.words == 1:
+            return [int(x) for x in arr]
+        return [int(lo) | (int(hi) << 64) for lo, hi in arr.reshape(-1, 2)]
+
+    # ---- table read-back
+    def moves(self):
+        """(k[L,5], dest[L,5,3], prob[L,5,3], cells_rc[L,2]) -- single_agent_movements for every (cell, action)."""
+        if self._moves is None:
+            k = np.zeros((self.L, 5), np.uint8)
+            dest = np.zeros((self.L, 5, 3), np.int32)
+            prob = np.zeros((self.L, 5, 3), np.float64)
+            rc = np.zeros((self.L, 2), np.int32)
+            check(lib().mapf_ctx_moves(self._h, _ptr(k), _ptr(dest), _ptr(prob), _ptr(rc)))
+            self._moves = (k, dest, prob, rc)
+        return self._moves
+
+    # ---- bulk encodings
+    def decode(self, states):
+        import torch
+        B = states.shape[0]
+        cells = torch.empty((B, self.n), dtype=torch.int32, device=self.torch_device)
+        check(lib().mapf_decode_states(self._h, _ptr(states), B, _ptr(cells), self._stream()))
+        return cells
+
+    def encode(self, cells):
+        B = cells.shape[0]
+        states = self.new_states(B)
+        check(lib().mapf_encode_states(self._h, _ptr(cells), B, _ptr(states), self._stream()))
+        return states
+
+    # ---- P[s][a] rows
+    def _scan(self, row_len):
+        import torch
+        B = row_len.shape[0]
+        row_ptr = torch.empty(B + 1, dtype=torch.int64, device=self.torch_device)
+        scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_scan_rows(self._h, _ptr(row_len), B, _ptr(row_ptr), _ptr(scratch), self._stream()))
+        return row_ptr
+
+    def _alloc_records(self, total):
+        import torch
+        dev = self.torch_device
+        return (self.new_states(total), torch.empty(total, dtype=torch.float64, device=dev),
+                torch.empty(total, dtype=torch.float64, device=dev), torch.empty(total, dtype=torch.uint8, device=dev))
+
+    def transitions(self, states, actions):
+        """CSR expansion of P[states[b]][actions[b]] -> (row_ptr, next_state, prob, reward, flags), all on device."""
+        import torch
+        B = states.shape[0]
+        row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_count_rows(self._h, _ptr(states), _ptr(actions), B, _ptr(row_len), self._stream()))
+        row_ptr = self._scan(row_len)
+        total = int(row_ptr[-1].item())
+        ns, prob, reward, flags = self._alloc_records(total)
+        check(lib().mapf_expand(self._h, _ptr(states), _ptr(actions), B, _ptr(row_ptr), _ptr(ns), _ptr(prob),
+                                _ptr(reward), _ptr(flags), self._stream()))
+        return row_ptr, ns, prob, reward, flags
+
+    def table_range(self, s_begin, n_states):
+        """The slab [s_begin, s_begin + n_states) x [0, nA) of the full table, rows in (s, a) order."""
+        import torch
+        sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
+        B = n_states * self.nA
+        row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_count_range(self._h, C.byref(sb), n_states, _ptr(row_len), self._stream()))
+        row_ptr = self._scan(row_len)
+        total = int(row_ptr[-1].item())
+        ns, prob, reward, flags = self._alloc_records(total)
+        check(lib().mapf_expand_range(self._h, C.byref(sb), n_states, _ptr(row_ptr), _ptr(ns), _ptr(prob), _ptr(reward),
+                                      _ptr(flags), self._stream()))
+        return row_ptr, ns, prob, reward, flags
+
+    def checksum(self, ns, prob, reward, flags, index_base=0, out=None):
+        import torch
+        if out is None:
+            out = torch.zeros(8, dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_checksum(self._h, prob.shape[0], index_base, _ptr(ns), _ptr(prob), _ptr(reward), _ptr(flags),
+                                  _ptr(out), self._stream()))
+        return out
+
+    # ---- step / rollout
+    def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None):
+        import torch
+        B = states.shape[0]
+        dev = self.torch_device
+        if out is None:
+            out = (self.new_states(B), torch.empty(B, dtype=torch.float64, device=dev),
+                   torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.bool, device=dev),
+                   torch.empty(B, dtype=torch.bool, device=dev))
+        ns, reward, prob, done, coll = out
+        check(lib().mapf_step(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
+                              OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
+                              _ptr(coll), self._stream()))
+        return out
+
+    def rollout(self, states, actions, T, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=True, out=None):
+        import torch
+        B = states.shape[0]
+        dev = self.torch_device
+        if out is None:
+            out = (torch.empty((T,) + self.state_shape(B), dtype=torch.int64, device=dev),
+                   torch.empty((T, B), dtype=torch.float64, device=dev),
+                   torch.empty((T, B), dtype=torch.float64, device=dev),
+                   torch.empty((T, B), dtype=torch.bool, device=dev), torch.empty((T, B), dtype=torch.bool, device=dev))
+        ns, reward, prob, done, coll = out
+        check(lib().mapf_rollout(self._h, _ptr(states), _ptr(actions), T, B, _ptr(uniforms), seed, step_index,
+                                 env_offset, OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob),
+                                 _ptr(done), _ptr(coll), self._stream()))
+        return out
+
+    def step_host(self, states, actions, out, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False):
+        """Host-buffer step (numpy arrays or pinned CPU tensors in, the five results written into `out`)."""
+        ns, reward, prob, done, coll = out
+        B = actions.shape[0]
+        check(lib().mapf_step_host(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
+                                   OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
+                                   _ptr(coll)))
+        return out

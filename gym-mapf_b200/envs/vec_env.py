@@ -1,0 +1,118 @@
+"""VecMapfEnv -- B independent copies of one MapfEnv spec, stepped and expanded in bulk on one GPU.
+
+This is the batched surface the reference lacks: the same transition model as `MapfEnv.step` /
+`MapfEnv.P` (reference mapf_env.py:237-266, 448-479), over device-resident tensors.
+
+State tensors are `int64[B]` when L**n < 2**63, else `int64[B, 2]` (low word, high word).  Actions are `int32[B]`
+base-5 joint actions.  Rewards / probabilities are float64, dones / collisions are bool.
+"""
+import collections
+
+import numpy as np
+
+Transitions = collections.namedtuple("Transitions", "row_ptr next_state prob reward flags")
+Rollout = collections.namedtuple("Rollout", "next_state reward prob done collision")
+
+
+class VecMapfEnv:
+    def __init__(self, env, num_envs, device=None, seed=0, auto_reset=True):
+        """`env`: a MapfEnv (its spec and device context are shared).  `seed` keys the Philox sampling stream;
+        `auto_reset`: an env whose step returns done restarts from the start state (its returned next state is then
+        the start state, as in gym's vector envs)."""
+        import torch
+        self.env = env
+        if device is not None and env._engine_obj is None:
+            env.device = device
+        self.engine = env.engine
+        self.device = self.engine.torch_device
+        self.num_envs = int(num_envs)
+        self.seed = int(seed)
+        self.auto_reset = bool(auto_reset)
+        self.env_offset = 0      # index of this shard's first env in a sharded global batch
+        self.step_count = 0
+        self.n_agents, self.nS, self.nA = env.n_agents, env.nS, env.nA
+        self.states = self.engine.new_states(self.num_envs)
+        self._torch = torch
+        self.reset()
+
+    # ---- encodings ---------------------------------------------------------------------------------------------
+    def state_to_cells(self, states):
+        """int32[B, n] per-agent cell ids (bulk `state_to_locations`, reference mapf_env.py:358-362)."""
+        return self.engine.decode(states)
+
+    def cells_to_state(self, cells):
+        """Bulk `locations_to_state` (reference mapf_env.py:364-371) from int32[B, n] cell ids."""
+        return self.engine.encode(cells.to(self._torch.int32).contiguous())
+
+    def states_from_ints(self, values):
+        return self.engine.states_from_ints(values)
+
+    def states_to_ints(self, states):
+        return self.engine.states_to_ints(states)
+
+    # ---- episode control ---------------------------------------------------------------------------------------
+    def reset(self):
+        """Every env back on the start state (reference mapf_env.py:290-293).  Returns the state tensor."""
+        s0 = self.engine.states_from_ints([self.engine.s0])
+        self.states.copy_(s0.expand_as(self.states) if self.engine.words == 1 else s0.expand(self.num_envs, 2))
+        return self.states
+
+    def set_states(self, states):
+        self.states.copy_(states)
+
+    # ---- sampled transitions -----------------------------------------------------------------------------------
+    def step(self, actions, uniforms=None):
+        """One joint step of every env.  Returns (next_states, rewards, dones, info) with
+        info = {"prob": f64[B], "collision": bool[B]}.  `uniforms` (f64[B, n]) replays given draws bit-exactly;
+        without it the device-side Philox stream keyed by (seed, env, step) is used."""
+        ns, reward, prob, done, coll = self.engine.step(
+            self.states, actions, uniforms=uniforms, seed=self.seed, step_index=self.step_count,
+            env_offset=self.env_offset, auto_reset=self.auto_reset)
+        self.states = ns
+        self.step_count += 1
+        return ns, reward, done, {"prob": prob, "collision": coll}
+
+    def rollout(self, T, actions=None, uniforms=None):
+        """T steps in one launch.  `actions`: int32[T, B] or None for a uniformly random policy.  Returns a Rollout
+        of step-major [T, B] tensors; the env states advance by T steps."""
+        out = self.engine.rollout(self.states, actions, T, uniforms=uniforms, seed=self.seed,
+                                  step_index=self.step_count, env_offset=self.env_offset, auto_reset=self.auto_reset)
+        self.step_count += T
+        return Rollout(*out)
+
+    def step_host(self, actions, out=None, uniforms=None):
+        """End-to-end host path: `actions` is a CPU int32 array/tensor; the env states are read from and written
+        back to a host mirror, and the five results land in host memory (numpy arrays, or `out`)."""
+        B = self.num_envs
+        if not hasattr(self, "_host_states"):
+            self._host_states = self._torch.empty(self.states.shape, dtype=self._torch.int64).pin_memory()
+            self._host_states.copy_(self.states)
+        if out is None:
+            out = (self._torch.empty(self.states.shape, dtype=self._torch.int64).pin_memory(),
+                   self._torch.empty(B, dtype=self._torch.float64).pin_memory(),
+                   self._torch.empty(B, dtype=self._torch.float64).pin_memory(),
+                   self._torch.empty(B, dtype=self._torch.bool).pin_memory(),
+                   self._torch.empty(B, dtype=self._torch.bool).pin_memory())
+        self.engine.step_host(self._host_states, actions, out, uniforms=uniforms, seed=self.seed,
+                              step_index=self.step_count, env_offset=self.env_offset, auto_reset=self.auto_reset)
+        self._host_states, out = out[0], (self._host_states,) + tuple(out[1:])
+        self.step_count += 1
+        return (self._host_states,) + tuple(out[1:])
+
+    # ---- transition table --------------------------------------------------------------------------------------
+    def transitions(self, states, actions):
+        """P[s][a] for B pairs as CSR: records row_ptr[b] .. row_ptr[b+1] are the row of pair b, in the
+        reference's order.  flags bit 0 = done, bit 1 = collision."""
+        return Transitions(*self.engine.transitions(states, actions))
+
+    def build_table(self, s_begin, n_states):
+        """The table slab [s_begin, s_begin + n_states) x [0, nA): row index = (s - s_begin) * nA + a."""
+        return Transitions(*self.engine.table_range(int(s_begin), int(n_states)))
+
+    def checksum(self, tr, index_base=0):
+        """dict of mod-2**64 checksums of a Transitions (see include/mapf_b200.h: mapf_checksum)."""
+        out = self.engine.checksum(tr.next_state, tr.prob, tr.reward, tr.flags, index_base=index_base)
+        v = out.cpu().numpy().view(np.uint64)
+        keys = ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi", "sum_prob_bits", "sum_reward_bits",
+                "ordered"]
+        return dict(zip(keys, (int(x) for x in v)))

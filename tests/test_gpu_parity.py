@@ -1,0 +1,312 @@
+"""GPU parity: the CUDA path (through the C ABI, include/mapf_b200.h) against the reference-generated golden
+fixtures and against the C oracle on seeded inputs.  Integer fields and fp64 bit patterns must be identical."""
+import numpy as np
+import pytest
+
+import golden_util as G
+from engine_util import (make_engine, make_oracle, states_tensor, split_states, u64, assert_rows_equal)
+
+pytestmark = pytest.mark.gpu
+
+ROWS = G.names("rows_")
+STEPS = G.names("steps_")
+MOVES = G.names("moves_")
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+@pytest.mark.parametrize("name", ROWS)
+def test_expand_matches_reference_rows(name, torch):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    assert eng.L == spec["L"] and str(eng.nS) == spec["nS"] and str(eng.s0) == spec["s0"] and eng.nA == spec["nA"]
+    states = states_tensor(eng, d["state_lo"], d["state_hi"])
+    actions = torch.from_numpy(d["action"].astype(np.int32)).to(eng.torch_device)
+    got = eng.transitions(states, actions)
+    assert_rows_equal(eng, got, d["row_ptr"], d["next_lo"], d["next_hi"], d["prob_bits"], d["reward_bits"], d["done"],
+                      d["collision"])
+    # checksum kernel agrees with the host definition
+    cs = eng.checksum(got[1], got[2], got[3], got[4]).cpu().numpy().view(np.uint64)
+    want = G.checksums(d["next_lo"], d["next_hi"], d["prob_bits"], d["reward_bits"], d["done"], d["collision"])
+    keys = ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi", "sum_prob_bits", "sum_reward_bits", "ordered"]
+    assert {k: int(v) for k, v in zip(keys, cs)} == want
+
+
+@pytest.mark.parametrize("name", G.names("full_"))
+def test_full_table_c1(name, torch):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    nS = int(spec["nS"])
+    row_ptr, ns, prob, reward, flags = eng.table_range(0, nS)
+    assert np.array_equal(np.diff(row_ptr.cpu().numpy()).astype(np.uint8), d["row_len"])
+    cs = eng.checksum(ns, prob, reward, flags).cpu().numpy().view(np.uint64)
+    keys = ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi", "sum_prob_bits", "sum_reward_bits", "ordered"]
+    for k, v in zip(keys, cs):
+        assert int(v) == int(d[k]), k
+    assert int(cs[0]) == 669808
+    # and record by record against the oracle
+    ora = make_oracle(spec)
+    s = np.repeat(np.arange(nS, dtype=np.uint64), spec["nA"])
+    a = np.tile(np.arange(spec["nA"], dtype=np.int64), nS)
+    w = ora.rows(s, np.zeros_like(s), a)
+    assert_rows_equal(eng, (row_ptr, ns, prob, reward, flags), w["row_ptr"], w["next_lo"], w["next_hi"],
+                      G.f64_to_bits(w["prob"]), G.f64_to_bits(w["reward"]), w["done"], w["collision"])
+    # the slab split in two must concatenate to the same table
+    half = nS // 2
+    a_ptr, a_ns, *_ = eng.table_range(0, half)
+    b_ptr, b_ns, *_ = eng.table_range(half, nS - half)
+    assert int(a_ptr[-1]) + int(b_ptr[-1]) == 669808
+    assert torch.equal(torch.cat([a_ns, b_ns]), ns)
+
+
+@pytest.mark.parametrize("name", STEPS)
+def test_step_matches_reference_traces(name, torch):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    states = states_tensor(eng, d["state_lo"], d["state_hi"])
+    actions = torch.from_numpy(d["action"].astype(np.int32)).to(eng.torch_device)
+    uniforms = torch.from_numpy(G.bits_to_f64(d["uniform_bits"]).copy()).to(eng.torch_device)
+    ns, reward, prob, done, coll = eng.step(states, actions, uniforms=uniforms)
+    lo, hi = split_states(eng, ns)
+    assert np.array_equal(lo, d["next_lo"]) and np.array_equal(hi, d["next_hi"])
+    assert np.array_equal(u64(reward), d["reward_bits"]) and np.array_equal(u64(prob), d["prob_bits"])
+    assert np.array_equal(done.cpu().numpy().astype(np.uint8), d["done"])
+    assert np.array_equal(coll.cpu().numpy().astype(np.uint8), d["collision"])
+    # in place (next_states aliasing states) gives the same answer
+    st2 = states.clone()
+    out = (st2, torch.empty_like(reward), torch.empty_like(prob), torch.empty_like(done), torch.empty_like(coll))
+    eng.step(st2, actions, uniforms=uniforms, out=out)
+    assert torch.equal(st2, ns) and torch.equal(out[1], reward)
+
+
+@pytest.mark.parametrize("name", MOVES)
+def test_move_table_matches_reference(name):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    k, dest, prob, rc = eng.moves()
+    assert np.array_equal(k, d["k"]) and np.array_equal(dest, d["dest"])
+    assert np.array_equal(G.f64_to_bits(prob), d["prob_bits"])
+    assert np.array_equal(rc, d["cells"])
+
+
+@pytest.mark.parametrize("name", ["rows_c2", "rows_c4", "rows_c5_n10", "rows_berlin", "rows_obst4_n3_v0_soc"])
+def test_encode_decode_roundtrip(name, torch):
+    spec, _ = G.load(name)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(5)
+    B = 20000
+    cells = rng.integers(0, eng.L, (B, eng.n)).astype(np.int32)
+    lo, hi = ora.encode(cells)
+    t = eng.encode(torch.from_numpy(cells).to(eng.torch_device))
+    glo, ghi = split_states(eng, t)
+    assert np.array_equal(glo, lo) and np.array_equal(ghi, hi)
+    back = eng.decode(t).cpu().numpy()
+    assert np.array_equal(back, cells)
+    # extremes: state 0 and nS - 1
+    ext = eng.states_from_ints([0, eng.nS - 1, eng.s0, eng.goal_state])
+    dec = eng.decode(ext).cpu().numpy()
+    assert np.all(dec[0] == 0) and np.all(dec[1] == eng.L - 1)
+    assert eng.states_to_ints(eng.encode(torch.from_numpy(dec).to(eng.torch_device))) == [0, eng.nS - 1, eng.s0,
+                                                                                         eng.goal_state]
+
+
+@pytest.mark.parametrize("name,B", [("rows_c2", 1 << 20), ("rows_c4", 1 << 17), ("rows_c3", 1 << 18),
+                                    ("rows_c5_n10", 1 << 15), ("rows_berlin", 1 << 17)])
+def test_step_large_batch_vs_oracle(name, B, torch):
+    """BASELINE.json sizes (C2: 2**20 envs): every env-step compared bit-exactly against the C oracle."""
+    spec, _ = G.load(name)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(17)
+    n, L = eng.n, eng.L
+    # a third uniformly random states, a third inside a small id window (dense conflicts), a third near the goal
+    cells = rng.integers(0, L, (B, n)).astype(np.int32)
+    base = rng.integers(0, max(1, L - 6), B)
+    dense = (base[:, None] + rng.integers(0, 6, (B, n))).astype(np.int32)
+    cells[B // 3: 2 * B // 3] = dense[B // 3: 2 * B // 3]
+    goal = ora.decode(np.array([eng.goal_state & ((1 << 64) - 1)], np.uint64),
+                      np.array([eng.goal_state >> 64], np.uint64))[0]
+    near = np.tile(goal, (B, 1))
+    jitter = rng.integers(0, n, B)
+    near[np.arange(B), jitter] = rng.integers(0, L, B)
+    cells[2 * B // 3:] = near[2 * B // 3:]
+    lo, hi = ora.encode(cells)
+    actions = rng.integers(0, eng.nA, B).astype(np.int64)
+    actions[::7] = 0
+    uniforms = rng.random((B, n))
+    want = ora.step(lo, hi, actions, uniforms, threads=8)
+    states = states_tensor(eng, lo, hi)
+    ns, reward, prob, done, coll = eng.step(states, torch.from_numpy(actions.astype(np.int32)).to(eng.torch_device),
+                                            uniforms=torch.from_numpy(uniforms).to(eng.torch_device))
+    glo, ghi = split_states(eng, ns)
+    assert np.array_equal(glo, want["next_lo"]) and np.array_equal(ghi, want["next_hi"])
+    assert np.array_equal(u64(reward), G.f64_to_bits(want["reward"]))
+    assert np.array_equal(u64(prob), G.f64_to_bits(want["prob"]))
+    assert np.array_equal(done.cpu().numpy().astype(np.uint8), want["done"])
+    assert np.array_equal(coll.cpu().numpy().astype(np.uint8), want["collision"])
+    assert want["collision"].sum() > 0 and want["terminal"].sum() > 0 and (want["done"] & ~want["collision"]).sum() > 0
+
+
+@pytest.mark.parametrize("name,B", [("rows_c2", 200000), ("rows_c4", 600), ("rows_c3", 20000), ("rows_c5_n7", 4000),
+                                    ("rows_berlin", 100000)])
+def test_expand_large_batch_vs_oracle(name, B, torch):
+    spec, _ = G.load(name)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(23)
+    n, L = eng.n, eng.L
+    cells = rng.integers(0, L, (B, n)).astype(np.int32)
+    base = rng.integers(0, max(1, L - 5), B)
+    dense = (base[:, None] + rng.integers(0, 5, (B, n))).astype(np.int32)
+    cells[::2] = dense[::2]
+    lo, hi = ora.encode(cells)
+    actions = rng.integers(0, eng.nA, B).astype(np.int64)
+    want = ora.rows(lo, hi, actions, threads=8)
+    got = eng.transitions(states_tensor(eng, lo, hi), torch.from_numpy(actions.astype(np.int32)).to(eng.torch_device))
+    assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                      G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+    # size-independent property: every row's probabilities sum to 1 (within fp64 rounding of a <=3**n-term sum)
+    row_ptr, _, prob, _, _ = got
+    sums = torch.zeros(B, dtype=torch.float64, device=eng.torch_device)
+    rows = torch.repeat_interleave(torch.arange(B, device=eng.torch_device), row_ptr[1:] - row_ptr[:-1])
+    sums.index_add_(0, rows, prob)
+    assert float((sums - 1.0).abs().max()) < 1e-9
+
+
+def test_table_range_slab_c3(torch):
+    """C3-style slab: consecutive joint states x all 15 625 actions of maze-32-32-4 (6 agents), vs the oracle."""
+    spec, _ = G.load("rows_c3")
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    s_begin = int(spec["nS"]) // 8 * 3 + 12345
+    n_states = 3
+    got = eng.table_range(s_begin, n_states)
+    want = ora.table_checksums(s_begin, n_states)
+    cs = eng.checksum(got[1], got[2], got[3], got[4]).cpu().numpy().view(np.uint64)
+    keys = ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi", "sum_prob_bits", "sum_reward_bits", "ordered"]
+    assert {k: int(v) for k, v in zip(keys, cs)} == want
+
+
+def test_rollout_equals_repeated_steps(torch):
+    spec, _ = G.load("rows_c2")
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(3)
+    B, T, n = 5000, 12, eng.n
+    actions = rng.integers(0, eng.nA, (T, B)).astype(np.int32)
+    uniforms = rng.random((T, B, n))
+    for auto_reset in (False, True):
+        states = eng.states_from_ints([eng.s0] * B)
+        out = eng.rollout(states, torch.from_numpy(actions).to(eng.torch_device), T,
+                          uniforms=torch.from_numpy(uniforms).to(eng.torch_device), auto_reset=auto_reset)
+        cur_lo = np.full(B, eng.s0, dtype=np.uint64)
+        zeros = np.zeros(B, np.uint64)
+        for t in range(T):
+            w = ora.step(cur_lo, zeros, actions[t].astype(np.int64), uniforms[t])
+            nxt = w["next_lo"].copy()
+            if auto_reset:
+                nxt[w["done"] == 1] = eng.s0
+            assert np.array_equal(u64(out[0][t]), nxt), (auto_reset, t)
+            assert np.array_equal(u64(out[1][t]), G.f64_to_bits(w["reward"]))
+            assert np.array_equal(u64(out[2][t]), G.f64_to_bits(w["prob"]))
+            assert np.array_equal(out[3][t].cpu().numpy().astype(np.uint8), w["done"])
+            assert np.array_equal(out[4][t].cpu().numpy().astype(np.uint8), w["collision"])
+            cur_lo = nxt
+        assert np.array_equal(u64(states), cur_lo)
+
+
+def philox4x32_10(c, k):
+    """numpy restatement of Philox4x32-10 (Salmon et al. 2011) for checking the device stream."""
+    c = [np.asarray(x, dtype=np.uint64) for x in c]
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c = [(hi1 ^ c[1] ^ k0) & m32, lo1, (hi0 ^ c[3] ^ k1) & m32, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    out = philox4x32_10([0, 0, 0, 0], [0, 0])
+    assert [int(x) for x in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    out = philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)
+    assert [int(x) for x in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])
+    assert [int(x) for x in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+@pytest.mark.parametrize("name", ["rows_c2", "rows_c5_n7"])
+def test_device_sampling_stream(name, torch):
+    """Perf mode (uniforms=None): the device draws agent i's uniform as word i%4 of Philox block i//4 at counter
+    (env_offset + env, step).  Replaying those uniforms through the oracle must give the same step."""
+    spec, _ = G.load(name)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    B, n = 50000, eng.n
+    seed, step_index, env_offset = 0x123456789abcdef, (5 << 32) | 77, 1 << 33
+    rng = np.random.default_rng(9)
+    cells = rng.integers(0, eng.L, (B, n)).astype(np.int32)
+    lo, hi = ora.encode(cells)
+    actions = rng.integers(0, eng.nA, B).astype(np.int64)
+    env = np.arange(B, dtype=np.uint64) + np.uint64(env_offset)
+    uniforms = np.zeros((B, n))
+    for blk in range((n + 3) // 4):
+        words = philox4x32_10([env & np.uint64(0xFFFFFFFF), env >> np.uint64(32),
+                               np.full(B, step_index & 0xFFFFFFFF, np.uint64),
+                               np.full(B, ((step_index >> 32) << 8) | blk, np.uint64)],
+                              [seed & 0xFFFFFFFF, seed >> 32])
+        for q in range(4):
+            if blk * 4 + q < n:
+                uniforms[:, blk * 4 + q] = words[q].astype(np.float64) * 2.0 ** -32
+    want = ora.step(lo, hi, actions, uniforms)
+    ns, reward, prob, done, coll = eng.step(states_tensor(eng, lo, hi),
+                                            torch.from_numpy(actions.astype(np.int32)).to(eng.torch_device),
+                                            seed=seed, step_index=step_index, env_offset=env_offset)
+    glo, ghi = split_states(eng, ns)
+    assert np.array_equal(glo, want["next_lo"]) and np.array_equal(ghi, want["next_hi"])
+    assert np.array_equal(u64(prob), G.f64_to_bits(want["prob"]))
+    assert np.array_equal(u64(reward), G.f64_to_bits(want["reward"]))
+    # slip frequencies: with fail_prob 0.2 an unobstructed agent keeps its intended move 80% of the time
+    frac = float((want["prob"] > 0).mean())
+    assert frac > 0.5
+
+
+def test_errors_and_edge_cases(torch):
+    from gym_mapf_b200 import _native
+    spec, _ = G.load("rows_obst4_n2_v0_soc")
+    obst = np.array([[1 if ch == "@" else 0 for ch in row] for row in spec["rows"]], dtype=np.uint8)
+    with pytest.raises(KeyError):  # start on an obstacle (reference: KeyError from loc_to_int, mapf_env.py:369)
+        _native.Engine(obst, 2, [[0, 2], [3, 2]], spec["goals"], 0.2, -1000.0, 100.0, -1.0, False)
+    with pytest.raises(KeyError):  # goal off the grid
+        _native.Engine(obst, 2, spec["starts"], [[9, 9], [0, 1]], 0.2, -1000.0, 100.0, -1.0, False)
+    with pytest.raises(_native.NativeError):
+        _native.Engine(obst, 14, [[0, 0]] * 14, [[0, 0]] * 14, 0.2, -1000.0, 100.0, -1.0, False)
+    eng = make_engine(spec)
+    # empty batches
+    empty_s = eng.new_states(0)
+    empty_a = torch.empty(0, dtype=torch.int32, device=eng.torch_device)
+    row_ptr, ns, prob, reward, flags = eng.transitions(empty_s, empty_a)
+    assert row_ptr.tolist() == [0] and ns.numel() == 0
+    out = eng.step(empty_s, empty_a)
+    assert out[0].numel() == 0
+    # ragged sizes around warp / block boundaries
+    ora = make_oracle(spec)
+    for B in (1, 31, 32, 33, 255, 257, 2049):
+        rng = np.random.default_rng(B)
+        lo = rng.integers(0, eng.nS, B).astype(np.uint64)
+        a = rng.integers(0, eng.nA, B).astype(np.int64)
+        want = ora.rows(lo, np.zeros_like(lo), a)
+        got = eng.transitions(states_tensor(eng, lo, np.zeros_like(lo)),
+                              torch.from_numpy(a.astype(np.int32)).to(eng.torch_device))
+        assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                          G.f64_to_bits(want["reward"]), want["done"], want["collision"])
