@@ -257,8 +257,9 @@ def run_ours(args):
         e1.record()
         barrier()
         reps_ms.append(e0.elapsed_time(e1))
-        if len(reps_ms) >= args.reps or (args.reps == 0 and time.time() - t_wall0 > args.min_seconds
-                                         and len(reps_ms) >= 3):
+        if args.reps > 0 and len(reps_ms) >= args.reps:
+            break
+        if args.reps == 0 and len(reps_ms) >= 3 and time.time() - t_wall0 > args.min_seconds:
             break
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -285,7 +286,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> step -> D2H, every step
     e2e = None
-    if rank == 0 or world > 1:
+    if not args.no_e2e:
         hs = torch.empty(eng.state_shape(B), dtype=torch.int64).pin_memory()
         hs.copy_(states[0])
         ha = actions[0].cpu().pin_memory()
@@ -341,6 +342,7 @@ def main():
     ap.add_argument("--reps", type=int, default=0, help="timed repetitions of the K-step region (0 = auto, >= ~1.5 s)")
     ap.add_argument("--min-seconds", type=float, default=1.5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libmapf_b200.so")
+LIB_PATH = os.environ.get("MAPF_B200_LIB", os.path.join(CSRC, "libmapf_b200.so"))  # override: tuning experiments
 
 MAPF_OK, MAPF_ERR_INVALID, MAPF_ERR_KEY, MAPF_ERR_UNSUPPORTED, MAPF_ERR_CUDA, MAPF_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 MAPF_SOC, MAPF_MAKESPAN = 0, 1

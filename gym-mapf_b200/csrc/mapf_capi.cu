@@ -6,12 +6,14 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <vector>
 
 #include "../../include/mapf_b200.h"
+#include "mapf_host.h"
 #include "mapf_kernels.cuh"
 
 typedef unsigned __int128 u128;
@@ -52,10 +54,6 @@ struct DeviceGuard {
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------
-struct KernelSet {
-    const void *step, *rollout, *expand, *expand_range, *count, *count_range, *decode, *encode;
-};
-
 struct mapf_ctx {
     DevSpec sp;
     mapf_info info;
@@ -63,8 +61,13 @@ struct mapf_ctx {
     int threads = 256;           // CTA size of the hot kernels
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
-    int grid_step = 0, grid_rollout = 0, grid_expand = 0, grid_expand_range = 0, grid_plain = 0;
+    int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout_tape = 0;
+    int grid_expand = 0, grid_expand_range = 0, grid_plain = 0;
     KernelSet ks;
+    u32 pat_triple[MAPF_MAX_PATTERNS];  // merge patterns (see PatternList)
+    int n_patterns = 0;
+    double probtab[8];                  // probability of a merged outcome, indexed by its candidate mask
+    bool philox_ok = true;              // every pattern's probabilities add up to 1: device-side sampling is exact
     u64 *d_lut = nullptr;
     u32 *d_cell_rc = nullptr, *d_colbits = nullptr, *d_colbase = nullptr;
     std::vector<u64> h_lut;
@@ -76,59 +79,50 @@ struct mapf_ctx {
     size_t d_stage_bytes = 0;
 };
 
-template <int N>
-static KernelSet kernels_for(bool luts) {
-    KernelSet k;
-    if (luts) {
-        k.step = (const void *)k_step<N, true>;
-        k.rollout = (const void *)k_rollout<N, true>;
-        k.expand = (const void *)k_expand<N, true, false>;
-        k.expand_range = (const void *)k_expand<N, true, true>;
-    } else {
-        k.step = (const void *)k_step<N, false>;
-        k.rollout = (const void *)k_rollout<N, false>;
-        k.expand = (const void *)k_expand<N, false, false>;
-        k.expand_range = (const void *)k_expand<N, false, true>;
-    }
-    k.count = (const void *)k_count<N, false>;
-    k.count_range = (const void *)k_count<N, true>;
-    k.decode = (const void *)k_decode<N>;
-    k.encode = (const void *)k_encode<N>;
-    return k;
-}
-
-template <int N>
-static size_t expand_slab_bytes() { return sizeof(ExpandSlab<N>); }
-
-static KernelSet pick_kernels(int n, bool luts, size_t *slab) {
-    switch (n) {
-#define CASE(N) case N: *slab = expand_slab_bytes<N>(); return kernels_for<N>(luts);
-        CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
-#undef CASE
-    }
-    *slab = 0;
-    return KernelSet();
+static bool pick_kernels(int n, int words, bool luts, KernelSet *ks) {
+#ifdef MAPF_ONLY_N  // experiment builds (tools/sweep_step.py): a single agent count
+#define CAT2_(a, b) a##b
+#define CAT2(a, b) CAT2_(a, b)
+    static mapf_kernels_fn table[MAPF_MAXN + 1] = {nullptr};
+    table[MAPF_ONLY_N] = CAT2(mapf_get_kernels_, MAPF_ONLY_N);
+    if (n != MAPF_ONLY_N) return false;
+#else
+    static const mapf_kernels_fn table[MAPF_MAXN + 1] = {
+        nullptr, mapf_get_kernels_1, mapf_get_kernels_2, mapf_get_kernels_3, mapf_get_kernels_4, mapf_get_kernels_5,
+        mapf_get_kernels_6, mapf_get_kernels_7, mapf_get_kernels_8, mapf_get_kernels_9, mapf_get_kernels_10,
+        mapf_get_kernels_11, mapf_get_kernels_12, mapf_get_kernels_13};
+#endif
+    if (n < 1 || n > MAPF_MAXN) return false;
+    table[n](words, luts ? 1 : 0, ks);
+    return ks->step_tape != nullptr;
 }
 
 static FastDiv make_fastdiv(u64 d) {
+    // branch-free form: q = mulhi(x, magic); q = (((x - q) >> 1) + q) >> shift, exact for every 64-bit x
     FastDiv f;
-    f.magic = 0; f.shift = 0; f.add = 0;
-    int fl = 63 - __builtin_clzll(d);
-    if ((d & (d - 1)) == 0) { f.shift = (u32)fl; return f; }
-    u128 num = (u128)1 << (64 + fl);
+    f.magic = 0; f.shift = 0; f.pad = 0;
+    if (d <= 1) return f;  // x >> 1 >> ... is never taken: d == 1 only occurs when every state is 0
+    const int fl = 63 - __builtin_clzll(d);
+    if ((d & (d - 1)) == 0) { f.shift = (u32)(fl - 1); return f; }  // magic 0: ((x >> 1) >> (fl - 1))
+    const u128 num = (u128)1 << (64 + fl);
     u64 proposed = (u64)(num / d);
-    u64 rem = (u64)(num % d);
-    u64 e = d - rem;
-    if (e < (1ull << fl)) {
-        f.shift = (u32)fl;
-    } else {
-        proposed += proposed;
-        u64 twice = rem + rem;
-        if (twice >= d || twice < rem) proposed += 1;
-        f.shift = (u32)fl;
-        f.add = 1;
-    }
+    const u64 rem = (u64)(num % d);
+    proposed += proposed;
+    const u64 twice = rem + rem;
+    if (twice >= d || twice < rem) proposed += 1;
     f.magic = proposed + 1;
+    f.shift = (u32)fl;
+    return f;
+}
+
+static Div32 make_div32(u32 d) {
+    // round-DOWN magic: umulhi(x, magic) >> shift is floor(x / d) or one less, for every 32-bit x
+    Div32 f;
+    const int fl = 31 - __builtin_clz(d);
+    f.shift = (u32)fl;
+    const u64 p = 1ull << (32 + fl);
+    const u64 m = p / d;
+    f.magic = (u32)(m > 0xffffffffull ? 0xffffffffull : m);
     return f;
 }
 
@@ -156,6 +150,30 @@ static int occupancy_grid(const void *fn, int threads, size_t smem, int sm_count
     if (per_sm < 1) return fail(MAPF_ERR_CUDA, "kernel does not fit on an SM (threads=%d smem=%zu)", threads, smem);
     *grid = per_sm * sm_count;
     return MAPF_OK;
+}
+
+// Every first-occurrence merge of the candidates that have positive probability (mapf_env.py:172-182), as
+// 9-bit mask triples; at most 5 exist (the set partitions of three candidates).
+static int enumerate_patterns(int cand_mask, u32 *triples) {
+    int count = 0;
+    for (int labels = 0; labels < 27; ++labels) {
+        int lab[3] = {labels % 3, (labels / 3) % 3, labels / 9};
+        u32 mask[3] = {0, 0, 0};
+        int dest[3] = {-1, -1, -1}, k = 0;
+        for (int j = 0; j < 3; ++j) {
+            if (!((cand_mask >> j) & 1)) continue;
+            int at = -1;
+            for (int q = 0; q < k; ++q)
+                if (dest[q] == lab[j] && at < 0) at = q;
+            if (at >= 0) mask[at] |= 1u << j;
+            else { dest[k] = lab[j]; mask[k] = 1u << j; ++k; }
+        }
+        const u32 t = mask[0] | (mask[1] << 3) | (mask[2] << 6);
+        bool seen = false;
+        for (int q = 0; q < count; ++q) seen = seen || triples[q] == t;
+        if (!seen && count < MAPF_MAX_PATTERNS) triples[count++] = t;
+    }
+    return count;
 }
 
 extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out) {
@@ -227,10 +245,25 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         nS *= (u128)L;
     }
     sp.words = nS < ((u128)1 << 63) ? 1 : 2;
+    sp.smax[0] = (u64)(nS - 1); sp.smax[1] = (u64)((nS - 1) >> 64);
     u64 nA = 1;
     for (int i = 0; i < n; ++i) nA *= 5;
     sp.nA = nA;
-    sp.divL = make_fastdiv((u64)L);
+    // decode plan: two digits (radix L*L < 2**32) per 64-bit division
+    {
+        const u64 ll = (u64)L * (u64)L;
+        sp.LL = (u32)ll;
+        sp.divLL = make_fastdiv(ll);
+        sp.divL = make_div32((u32)L);
+        u128 v = nS - 1;
+        for (int pass = 0; pass < 8; ++pass) {
+            int limbs = 1;
+            for (int w = 3; w >= 1; --w)
+                if ((v >> (32 * w)) != 0) { limbs = w + 1; break; }
+            sp.limbs[pass] = limbs;
+            v /= (u128)ll;
+        }
+    }
     u128 s0 = 0, sg = 0, mul = 1;
     for (int i = 0; i < n; ++i) {  // vector_to_integer (__init__.py:70-79)
         s0 += (u128)start_id[i] * mul;
@@ -249,12 +282,34 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         delete ctx;
         return fail(MAPF_ERR_INVALID, "fail_prob %g leaves no outcome with positive probability", spec->fail_prob);
     }
-    for (int m = 1; m < 8; ++m) {
+    ctx->probtab[0] = 0.0;
+    for (int m = 1; m < 8; ++m) {  // a merged outcome's probability: its candidates added in list order
         double s = 0.0;
         bool first = true;
         for (int j = 0; j < 3; ++j)
             if ((m >> j) & 1) { s = first ? cand[j] : s + cand[j]; first = false; }
-        sp.probtab[m] = s;
+        ctx->probtab[m] = s;
+    }
+    ctx->n_patterns = enumerate_patterns(sp.cand_mask, ctx->pat_triple);
+    for (int p = 0; p < ctx->n_patterns; ++p) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            const u32 m = (ctx->pat_triple[p] >> (3 * j)) & 7u;
+            const double pj = ctx->probtab[m];
+            sp.pp[p][j] = pj;
+            if (m) acc = j == 0 ? pj : acc + pj;  // np.cumsum: sequential fp64 adds (mapf_env.py:255)
+            sp.cum[p][j] = acc;
+            // largest 32-bit w with acc > w * 2**-32, i.e. w < acc * 2**32 (an exact scaling)
+            double x = ceil(acc * 4294967296.0);
+            if (x > 4294967296.0) x = 4294967296.0;
+            if (x < 1.0) x = 1.0;  // cannot happen: the first merged outcome has positive probability
+            sp.thr[p][j] = (u32)((u64)x - 1);
+        }
+        // the device-side sampling mode counts thresholds below the draw, which needs the pattern's last
+        // cumulative probability to reach 1 (within 2**-32): true whenever right_fail + left_fail <= 1
+        const int k = (ctx->pat_triple[p] & 7u ? 1 : 0) + ((ctx->pat_triple[p] >> 3) & 7u ? 1 : 0) +
+                      ((ctx->pat_triple[p] >> 6) & 7u ? 1 : 0);
+        if (sp.thr[p][k - 1] != 0xffffffffu) ctx->philox_ok = false;
     }
     // ---- rewards (mapf_env.py:225-235, 436-446), one entry per number of parked agents
     for (int k = 0; k <= n; ++k) {
@@ -277,6 +332,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     }
     const int sm_count = prop.multiProcessorCount;
     const size_t lut_bytes = (size_t)L * 5 * sizeof(u64);
+    const size_t lut_pad = (lut_bytes + 15) & ~(size_t)15;
+    sp.lut_bytes = (u32)lut_pad;
 #define CTX_TRY(expr)                                                                                  \
     do {                                                                                               \
         cudaError_t _e = (expr);                                                                       \
@@ -286,7 +343,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
             return _rc;                                                                                \
         }                                                                                              \
     } while (0)
-    CTX_TRY(cudaMalloc(&ctx->d_lut, (lut_bytes + 15) & ~(size_t)15));
+    CTX_TRY(cudaMalloc(&ctx->d_lut, lut_pad));
+    CTX_TRY(cudaMemset(ctx->d_lut, 0, lut_pad));
     CTX_TRY(cudaMalloc(&ctx->d_cell_rc, (size_t)L * sizeof(u32)));
     CTX_TRY(cudaMalloc(&ctx->d_colbits, colbits.size() * sizeof(u32)));
     CTX_TRY(cudaMalloc(&ctx->d_colbase, colbase.size() * sizeof(u32)));
@@ -300,8 +358,12 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         }
         if (bm_smem > 48 * 1024)
             CTX_TRY(cudaFuncSetAttribute(k_build_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        PatternList pats;
+        memset(&pats, 0, sizeof(pats));
+        pats.count = ctx->n_patterns;
+        for (int p = 0; p < ctx->n_patterns; ++p) pats.triple[p] = ctx->pat_triple[p];
         const int blocks = (H * W + 255) / 256 < sm_count * 4 ? (H * W + 255) / 256 : sm_count * 4;
-        k_build_moves<<<blocks, 256, bm_smem>>>(ctx->d_colbits, ctx->d_colbase, H, W, wpc, sp.cand_mask, ctx->d_lut,
+        k_build_moves<<<blocks, 256, bm_smem>>>(ctx->d_colbits, ctx->d_colbase, H, W, wpc, sp.cand_mask, pats, ctx->d_lut,
                                                 ctx->d_cell_rc);
         CTX_TRY(cudaGetLastError());
         CTX_TRY(cudaDeviceSynchronize());
@@ -312,28 +374,41 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     CTX_TRY(cudaMemcpy(ctx->h_cell_rc.data(), ctx->d_cell_rc, (size_t)L * sizeof(u32), cudaMemcpyDeviceToHost));
     sp.lut = ctx->d_lut;
 
-    // ---- launch geometry: stage the move table in shared memory when it leaves room for >= 1 CTA per SM
-    size_t slab = 0;
-    const size_t lut_pad = (lut_bytes + 15) & ~(size_t)15;
+    // ---- launch geometry: stage the move table in shared memory when it leaves room for the per-warp scratch
     const size_t smem_limit = (size_t)prop.sharedMemPerBlockOptin;
-    bool luts = MAPF_SMEM_SMALL_BYTES + lut_pad + 16 * expand_slab_bytes<MAPF_MAXN>() <= smem_limit;
-    ctx->threads = (luts && lut_pad > 64 * 1024) ? 512 : 256;
-    sp.lut_smem = luts ? 1 : 0;
-    ctx->ks = pick_kernels(n, luts, &slab);
-    ctx->smem_base = MAPF_SMEM_SMALL_BYTES + (luts ? lut_pad : 0);
-    ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * slab;
-    const void *big[4] = {ctx->ks.step, ctx->ks.rollout, ctx->ks.expand, ctx->ks.expand_range};
-    for (int i = 0; i < 4; ++i) {
-        const size_t need = i < 2 ? ctx->smem_base : ctx->smem_expand;
-        if (need > 48 * 1024) CTX_TRY(cudaFuncSetAttribute(big[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    }
-    int rc;
-    if ((rc = occupancy_grid(ctx->ks.step, ctx->threads, ctx->smem_base, sm_count, &ctx->grid_step)) ||
-        (rc = occupancy_grid(ctx->ks.rollout, ctx->threads, ctx->smem_base, sm_count, &ctx->grid_rollout)) ||
-        (rc = occupancy_grid(ctx->ks.expand, ctx->threads, ctx->smem_expand, sm_count, &ctx->grid_expand)) ||
-        (rc = occupancy_grid(ctx->ks.expand_range, ctx->threads, ctx->smem_expand, sm_count, &ctx->grid_expand_range))) {
+    KernelSet probe;
+    if (!pick_kernels(n, sp.words, true, &probe)) {
         mapf_ctx_destroy(ctx);
-        return rc;
+        return fail(MAPF_ERR_UNSUPPORTED, "no kernels for %d agents with %d-word states", n, sp.words);
+    }
+    ctx->threads = lut_pad > 64 * 1024 ? 512 : 256;
+    if (const char *e = getenv("MAPF_THREADS")) {  // tuning experiments only
+        const int t = atoi(e);
+        if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
+    }
+    const bool luts = MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.expand_slab_bytes <= smem_limit;
+    if (!luts) ctx->threads = 256;
+    sp.lut_smem = luts ? 1 : 0;
+    pick_kernels(n, sp.words, luts, &ctx->ks);
+    ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);
+    ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
+    struct { const void *fn; size_t smem; int *grid; } plan[] = {
+        {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
+        {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
+        {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
+        {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
+        {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
+        {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand},
+        {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range}};
+    for (auto &pl : plan) {
+        if (pl.smem > 48 * 1024)
+            CTX_TRY(cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        int rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
+        if (rc) { mapf_ctx_destroy(ctx); return rc; }
+        if (const char *e = getenv("MAPF_BLOCKS_PER_SM")) {  // tuning experiments only
+            const int bps = atoi(e);
+            if (bps >= 1 && bps * sm_count <= *pl.grid) *pl.grid = bps * sm_count;
+        }
     }
     ctx->grid_plain = sm_count * 8;
 
@@ -364,10 +439,11 @@ extern "C" int mapf_ctx_moves(const mapf_ctx *ctx, uint8_t *k, int32_t *dest, do
     for (int i = 0; i < L * 5; ++i) {
         const u64 e = ctx->h_lut[i];
         const int kk = (int)ENT_K(e);
+        const u32 pid = ENT_POFF(e) / 32u;
         if (k) k[i] = (uint8_t)kk;
         for (int j = 0; j < 3; ++j) {
-            if (dest) dest[i * 3 + j] = j < kk ? (int32_t)ENT_DEST(e, j) : -1;
-            if (prob) prob[i * 3 + j] = j < kk ? ctx->sp.probtab[ENT_MASK(e, j)] : 0.0;
+            if (dest) dest[i * 3 + j] = j < kk ? (int32_t)((e >> (16 * j)) & 0xffffu) : -1;
+            if (prob) prob[i * 3 + j] = j < kk ? ctx->sp.pp[pid][j] : 0.0;
         }
     }
     if (cells_rc)
@@ -517,6 +593,67 @@ extern "C" int mapf_checksum(const mapf_ctx *ctx, int64_t n_records, int64_t ind
     return MAPF_OK;
 }
 
+static inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+static PhiloxKeys make_keys(uint64_t seed) {
+    PhiloxKeys K;
+    u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        K.k[2 * r] = k0;
+        K.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return K;
+}
+
+#define MAPF_LAUNCH_MAX_ENVS (1ll << 30)  // kernels index envs with 32 bits; larger batches are split
+
+// Picks the step-kernel variant: replayed uniforms -> TAPE; otherwise the 2-envs-per-thread kernel with 128-bit
+// loads/stores when the batch is even and every buffer is suitably aligned, else the scalar one.
+static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, const double *uniforms,
+                       uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
+                       double *reward, double *prob, uint8_t *done, uint8_t *collision, cudaStream_t stream) {
+    if (!uniforms && !ctx->philox_ok)
+        return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
+    const size_t sw = (size_t)ctx->sp.words * 8;
+    static int force_ept = -1;
+    if (force_ept < 0) {
+        const char *e = getenv("MAPF_STEP_EPT");
+        force_ept = e ? atoi(e) : 0;
+    }
+    for (int64_t off = 0; off < B; off += MAPF_LAUNCH_MAX_ENVS) {
+        const int64_t nb64 = B - off < MAPF_LAUNCH_MAX_ENVS ? B - off : MAPF_LAUNCH_MAX_ENVS;
+        DevSpec sp = ctx->sp;
+        PhiloxKeys keys = make_keys(seed);
+        const void *a_states = (const unsigned char *)states + sw * off;
+        const int32_t *a_actions = actions + off;
+        const double *a_u = uniforms ? uniforms + (size_t)off * ctx->sp.n : nullptr;
+        void *a_ns = (unsigned char *)next_states + sw * off;
+        double *a_r = reward + off, *a_p = prob + off;
+        uint8_t *a_d = done + off, *a_c = collision + off;
+        u32 nb = (u32)nb64;
+        u64 st = step_index, e0 = (u64)(env_offset + off);
+        u32 op = options;
+        void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, &a_u, &st, &e0, &op, &a_ns, &a_r, &a_p, &a_d, &a_c};
+        const void *fn;
+        int grid;
+        if (uniforms) {
+            fn = ctx->ks.step_tape;
+            grid = grid_for(nb, ctx->threads, ctx->grid_step_tape);
+        } else if (force_ept != 1 && (nb & 1) == 0 && aligned(a_states, 16) && aligned(a_ns, 16) && aligned(a_actions, 8) &&
+                   aligned(a_r, 16) && aligned(a_p, 16) && aligned(a_d, 2) && aligned(a_c, 2)) {
+            fn = ctx->ks.step_philox2;
+            grid = grid_for(nb / 2, ctx->threads, ctx->grid_step2);
+        } else {
+            fn = ctx->ks.step_philox1;
+            grid = grid_for(nb, ctx->threads, ctx->grid_step1);
+        }
+        LAUNCH(fn, grid, ctx->threads, ctx->smem_base, stream, args);
+    }
+    return MAPF_OK;
+}
+
 extern "C" int mapf_step(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B,
                          const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
                          uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
@@ -525,13 +662,8 @@ extern "C" int mapf_step(const mapf_ctx *ctx, const void *states, const int32_t 
         return fail(MAPF_ERR_INVALID, "mapf_step: bad argument");
     if (B == 0) return MAPF_OK;
     DeviceGuard g(ctx->device);
-    DevSpec sp = ctx->sp;
-    u64 sd = seed, st = step_index, e0 = (u64)env_offset;
-    u32 op = options;
-    void *args[] = {&sp, &states, &actions, &B, &uniforms, &sd, &st, &e0, &op, &next_states, &reward, &prob, &done,
-                    &collision};
-    LAUNCH(ctx->ks.step, grid_for(B, ctx->threads, ctx->grid_step), ctx->threads, ctx->smem_base, stream, args);
-    return MAPF_OK;
+    return launch_step(ctx, states, actions, B, uniforms, seed, step_index, env_offset, options, next_states, reward, prob,
+                       done, collision, (cudaStream_t)stream);
 }
 
 extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32_t *actions, int64_t T, int64_t B,
@@ -542,13 +674,22 @@ extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32
         (B > 0 && T > 0 && (!states_inout || !next_states || !reward || !prob || !done || !collision)))
         return fail(MAPF_ERR_INVALID, "mapf_rollout: bad argument");
     if (B == 0 || T == 0) return MAPF_OK;
+    if (B > MAPF_LAUNCH_MAX_ENVS) return fail(MAPF_ERR_INVALID, "mapf_rollout: at most 2**30 envs per call");
+    if (!uniforms && !ctx->philox_ok)
+        return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
     DeviceGuard g(ctx->device);
     DevSpec sp = ctx->sp;
-    u64 sd = seed, st = step_index0, e0 = (u64)env_offset;
-    u32 op = options;
-    void *args[] = {&sp, &states_inout, &actions, &T, &B, &uniforms, &sd, &st, &e0, &op, &next_states, &reward, &prob,
+    PhiloxKeys keys = make_keys(seed);
+    u64 st = step_index0, e0 = (u64)env_offset;
+    u32 op = options, nb = (u32)B;
+    void *args[] = {&sp, &keys, &states_inout, &actions, &T, &nb, &uniforms, &st, &e0, &op, &next_states, &reward, &prob,
                     &done, &collision};
-    LAUNCH(ctx->ks.rollout, grid_for(B, ctx->threads, ctx->grid_rollout), ctx->threads, ctx->smem_base, stream, args);
+    if (uniforms)
+        LAUNCH(ctx->ks.rollout_tape, grid_for(B, ctx->threads, ctx->grid_rollout_tape), ctx->threads, ctx->smem_base,
+               stream, args);
+    else
+        LAUNCH(ctx->ks.rollout_philox, grid_for(B, ctx->threads, ctx->grid_rollout), ctx->threads, ctx->smem_base, stream,
+               args);
     return MAPF_OK;
 }
 
@@ -597,18 +738,11 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         if (uniforms)
             CUDA_TRY(cudaMemcpyAsync(d_u + (size_t)n * 8 * b0, (const unsigned char *)uniforms + (size_t)n * 8 * b0,
                                      (size_t)n * 8 * nb, cudaMemcpyHostToDevice, st));
-        DevSpec sp = ctx->sp;
-        const void *a_states = d_s + sw * b0;
-        const int32_t *a_actions = (const int32_t *)(d_a + 4 * b0);
-        const double *a_u = uniforms ? (const double *)(d_u + (size_t)n * 8 * b0) : nullptr;
-        void *a_ns = d_ns + sw * b0;
-        double *a_r = (double *)(d_r + 8 * b0), *a_p = (double *)(d_p + 8 * b0);
-        uint8_t *a_d = d_d + b0, *a_c = d_c + b0;
-        int64_t nbv = nb;
-        u64 sd = seed, stp = step_index, e0 = (u64)env_offset + (u64)b0;
-        u32 op = options;
-        void *args[] = {&sp, &a_states, &a_actions, &nbv, &a_u, &sd, &stp, &e0, &op, &a_ns, &a_r, &a_p, &a_d, &a_c};
-        LAUNCH(ctx->ks.step, grid_for(nb, ctx->threads, ctx->grid_step), ctx->threads, ctx->smem_base, st, args);
+        int rc = launch_step(ctx, d_s + sw * b0, (const int32_t *)(d_a + 4 * b0), nb,
+                             uniforms ? (const double *)(d_u + (size_t)n * 8 * b0) : nullptr, seed, step_index,
+                             env_offset + b0, options, d_ns + sw * b0, (double *)(d_r + 8 * b0), (double *)(d_p + 8 * b0),
+                             d_d + b0, d_c + b0, st);
+        if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)next_states + sw * b0, d_ns + sw * b0, sw * nb, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)reward + 8 * b0, d_r + 8 * b0, 8 * nb, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)prob + 8 * b0, d_p + 8 * b0, 8 * nb, cudaMemcpyDeviceToHost, st));

@@ -12,107 +12,155 @@ typedef unsigned char u8;
 
 #define MAPF_MAXN 13
 #define MAPF_REW_STRIDE 16  // reward table row: parked-agent count 0..13
+#define MAPF_MAX_PATTERNS 8
 
-// Exact unsigned 64-bit division by a run-time constant (Granlund-Montgomery round-up method).
+// Exact unsigned 64-bit division by a run-time constant d >= 1, branch-free (Granlund-Montgomery round-up method
+// with the 65-bit magic; a power of two uses magic 0): q = mulhi(x, magic); q = (((x - q) >> 1) + q) >> shift.
 struct FastDiv {
     u64 magic;
     u32 shift;
-    u32 add;  // 1: the 65-bit-magic fix-up path
+    u32 pad;
+};
+// Division of any 32-bit x by L: q = umulhi(x, magic) >> shift underestimates by at most one (round-down magic),
+// which one compare fixes.
+struct Div32 {
+    u32 magic;
+    u32 shift;
 };
 
 // Move-table entry for one (cell, intended action): what `single_agent_movements` returns (mapf_env.py:163-184).
-//   bits  0..15 / 16..31 / 32..47  destination cell of merged outcome 0 / 1 / 2
-//   bits 48..50 / 51..53 / 54..56  which of the candidates {intended=1, right-slip=2, left-slip=4} merged into it;
-//                                  the mask indexes probtab[], whose entries are the candidates' probabilities
-//                                  added in list order (mapf_env.py:177-179)
-//   bits 57..58                    k = number of merged outcomes (1..3)
-#define ENT_DEST(e, j) ((u32)((e) >> (16 * (j))) & 0xffffu)
-#define ENT_MASK(e, j) ((u32)((e) >> (48 + 3 * (j))) & 7u)
-#define ENT_K(e) ((u32)((e) >> 57) & 3u)
+//   bits  0..15 / 16..31 / 32..47  destination cell of merged outcome 0 / 1 / 2 (unused slots repeat slot 0)
+//   bits 48..55                    32 * merge pattern id: which of the candidates {intended, right-slip,
+//                                  left-slip} fell on the same cell.  It is the byte offset of the pattern's row in
+//                                  the per-pattern tables, whose probabilities are the candidates' added in list
+//                                  order (mapf_env.py:177-179)
+//   bits 56..57                    k = number of merged outcomes (1..3); bits 58..63 are zero
+#define ENT_K(e) ((u32)((e) >> 56) & 3u)
+#define ENT_POFF(e) ((u32)((e) >> 48) & 0xffu)
+// destination of merged outcome j (0..2): bytes 2j, 2j+1 of the entry, zero-extended.  The upper two selector
+// nibbles 0xF replicate the (always clear) sign bit of byte 7.
+__device__ __forceinline__ u32 ent_dest(u64 e, u32 j) {
+    u32 d;  // PTX prmt (not __byte_perm, which documents 3-bit selectors) for the sign-replicating selector nibbles
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"((u32)e), "r"((u32)(e >> 32)), "r"(0xFF10u + 0x22u * j));
+    return d;
+}
 
 // Everything a hot kernel needs about one env spec; passed by value as a kernel parameter (constant bank).
 struct DevSpec {
-    int n;         // agents
-    int L;         // free cells
-    int words;     // 64-bit words per joint state (1 or 2)
-    int soc;       // 1: sum-of-costs living reward (mapf_env.py:440-446)
-    int H, Wd;     // grid height / width
-    int lut_smem;  // 1: the move table is staged in shared memory
-    int cand_mask; // bit j set: candidate j (intended, right, left) has probability > 0 (mapf_env.py:172)
-    u64 nA;        // 5**n
-    FastDiv divL;  // division by L
-    u64 s0[2];     // start state
-    const u64 *lut;  // [L*5] move table, global memory
-    u16 goal[16];    // goal cell per agent (mapf_env.py:158)
+    int n;             // agents
+    int L;             // free cells
+    int words;         // 64-bit words per joint state (1 or 2)
+    int soc;           // 1: sum-of-costs living reward (mapf_env.py:440-446)
+    int H, Wd;         // grid height / width
+    int lut_smem;      // 1: the move table is staged in shared memory
+    int cand_mask;     // bit j set: candidate j (intended, right, left) has probability > 0 (mapf_env.py:172)
+    u32 LL;            // L*L: a joint state is decoded two agents at a time
+    u32 lut_bytes;     // size of the move table, padded to 16 B
+    int limbs[8];      // words==2: 32-bit limbs that can be non-zero before the k-th division by LL
+    u64 nA;            // 5**n
+    u64 smax[2];       // nS - 1
+    FastDiv divLL;     // division by L*L
+    Div32 divL;        // division by L of a two-digit chunk
+    u64 s0[2];         // start state
+    const u64 *lut;    // [L*5] move table, global memory
+    u16 goal[16];      // goal cell per agent (mapf_env.py:158)
     u16 start[16];
-    double probtab[8];                      // indexed by candidate mask
-    double reward[3 * MAPF_REW_STRIDE];     // [0: living, 1: clash + living, 2: goal + living][parked agents]
+    // per merge pattern, for merged outcome j = 0..2 (slot 3 pads to 16 / 32 bytes):
+    u32 thr[MAPF_MAX_PATTERNS][8];     // largest 32-bit draw w with cumsum_j > w * 2**-32 (32-byte rows)
+    double cum[MAPF_MAX_PATTERNS][4];  // np.cumsum of the merged probabilities (mapf_env.py:255)
+    double pp[MAPF_MAX_PATTERNS][4];   // merged probabilities
+    double reward[3 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living][parked agents]
 };
 
 __device__ __forceinline__ u64 fastdiv(u64 x, const FastDiv &d) {
-    if (d.magic == 0) return x >> d.shift;
-    u64 q = __umul64hi(x, d.magic);
-    if (d.add) {
-        u64 t = ((x - q) >> 1) + q;
-        return t >> d.shift;
-    }
-    return q >> d.shift;
+    const u64 q = __umul64hi(x, d.magic);
+    return (((x - q) >> 1) + q) >> d.shift;
+}
+// chunk -> (chunk % L, chunk / L)
+__device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &r) {
+    q = __umulhi(x, sp.divL.magic) >> sp.divL.shift;
+    r = x - q * (u32)sp.L;
+    if (r >= (u32)sp.L) { r -= (u32)sp.L; q += 1; }
 }
 
 // ---- joint state <-> per-agent cells: little-endian radix L, agent 0 least significant (__init__.py:50-79) ----
-template <int N>
+// The state is split into two-digit chunks (radix L*L < 2**32) with 64-bit divisions and each chunk into its two
+// digits with one 32-bit multiply-high division.
+template <int N, int WORDS>
 __device__ __forceinline__ void decode_state(const DevSpec &sp, u64 lo, u64 hi, int (&cell)[N]) {
-    const u32 L = (u32)sp.L;
-    if (sp.words == 1) {
+    constexpr int PAIRS = (N + 1) / 2;
+    u32 chunk[PAIRS];
+    if (WORDS == 1) {
         u64 x = lo;
 #pragma unroll
-        for (int i = 0; i < N - 1; ++i) {
-            u64 q = fastdiv(x, sp.divL);
-            cell[i] = (int)(x - q * L);
-            x = q;
+        for (int p = 0; p < PAIRS; ++p) {
+            if (p + 1 < PAIRS) {
+                const u64 q = fastdiv(x, sp.divLL);
+                chunk[p] = (u32)x - (u32)q * sp.LL;
+                x = q;
+            } else {
+                chunk[p] = (u32)x;
+            }
         }
-        cell[N - 1] = (int)min(x, (u64)(L - 1));  // out-of-range states are rejected on the host; stay in bounds
     } else {
-        // 128-bit / 32-bit long division over four 32-bit limbs (partial dividends stay below 2**48)
+        // 128-bit / LL long division over 32-bit limbs; a partial dividend (rem << 32 | limb) fits 64 bits
         u32 limb[4] = {(u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)};
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            u64 rem = 0;
+        for (int p = 0; p < PAIRS; ++p) {
+            if (p + 1 < PAIRS) {
+                u64 rem = 0;
+                const int nl = sp.limbs[p < 8 ? p : 7];
 #pragma unroll
-            for (int w = 3; w >= 0; --w) {
-                u64 cur = (rem << 32) | limb[w];
-                u64 q = fastdiv(cur, sp.divL);
-                rem = cur - q * L;
-                limb[w] = (u32)q;
+                for (int w = 3; w >= 0; --w) {
+                    if (w < nl) {
+                        const u64 cur = (rem << 32) | limb[w];
+                        const u64 q = fastdiv(cur, sp.divLL);
+                        rem = cur - q * sp.LL;
+                        limb[w] = (u32)q;
+                    }
+                }
+                chunk[p] = (u32)rem;
+            } else {
+                chunk[p] = limb[0];
             }
-            cell[i] = (int)rem;
         }
     }
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) {
+        if (2 * p + 1 < N) {
+            u32 q, r;
+            divmod_L(sp, chunk[p], q, r);
+            cell[2 * p] = (int)r;
+            cell[2 * p + 1] = (int)q;
+        } else {
+            cell[2 * p] = (int)chunk[p];
+        }
+    }
+    // an out-of-range state (rejected by the host API) can only corrupt the top digit: keep it a valid table index
+    cell[N - 1] = (int)min((u32)cell[N - 1], (u32)(sp.L - 1));
 }
 
-template <int N>
+template <int N, int WORDS>
 __device__ __forceinline__ void encode_state(const DevSpec &sp, const int (&cell)[N], u64 &lo, u64 &hi) {
-    const u64 L = (u64)sp.L;
-    if (sp.words == 1) {
-        u64 acc = (u64)cell[N - 1];
+    constexpr int PAIRS = (N + 1) / 2;
+    const u32 L = (u32)sp.L;
+    u64 alo = 0, ahi = 0;
 #pragma unroll
-        for (int i = N - 2; i >= 0; --i) acc = acc * L + (u64)cell[i];
-        lo = acc;
-        hi = 0;
-    } else {
-        u64 alo = (u64)cell[N - 1], ahi = 0;
-#pragma unroll
-        for (int i = N - 2; i >= 0; --i) {
-            u64 carry = __umul64hi(alo, L);
-            ahi = ahi * L + carry;
-            alo = alo * L;
-            u64 t = alo + (u64)cell[i];
+    for (int p = PAIRS - 1; p >= 0; --p) {
+        const u32 chunk = (2 * p + 1 < N) ? (u32)cell[2 * p + 1] * L + (u32)cell[2 * p] : (u32)cell[2 * p];
+        if (WORDS == 1) {
+            alo = alo * sp.LL + chunk;
+        } else {
+            const u64 carry = __umul64hi(alo, (u64)sp.LL);
+            ahi = ahi * sp.LL + carry;
+            alo = alo * sp.LL;
+            const u64 t = alo + chunk;
             ahi += (t < alo) ? 1ull : 0ull;
             alo = t;
         }
-        lo = alo;
-        hi = ahi;
     }
+    lo = alo;
+    hi = ahi;
 }
 
 template <int N>
@@ -138,15 +186,22 @@ __device__ __forceinline__ bool is_terminal(const DevSpec &sp, const int (&cell)
     return dup || all_goal;
 }
 
-// _is_collision_transition_from_local_states (mapf_env.py:378-389): swap or vertex conflict over all pairs
+// _is_collision_transition_from_local_states (mapf_env.py:378-389): swap or vertex conflict over all pairs.
+// Cells are 16-bit, so agent i's move is packed as prev | next << 16; agent j swaps with i exactly when
+// next_j | prev_j << 16 equals that word.
 template <int N>
 __device__ __forceinline__ bool has_clash(const int (&prev)[N], const int (&nxt)[N]) {
+    u32 fw[N], bw[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        fw[i] = __byte_perm((u32)prev[i], (u32)nxt[i], 0x5410);
+        bw[i] = __byte_perm((u32)nxt[i], (u32)prev[i], 0x5410);
+    }
     bool c = false;
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = i + 1; j < N; ++j)
-            c = c || (nxt[i] == nxt[j]) || (prev[i] == nxt[j] && prev[j] == nxt[i]);
+        for (int j = i + 1; j < N; ++j) c = c || (nxt[i] == nxt[j]) || (fw[i] == bw[j]);
     return c;
 }
 
@@ -165,14 +220,25 @@ __device__ __forceinline__ int parked_agents(const DevSpec &sp, const int (&prev
 struct Philox4 {
     u32 v[4];
 };
-__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1) {
+// The ten round keys (key + r * Weyl constants) are computed on the host once per launch and passed as a kernel
+// parameter, so each round is two wide multiplies and two three-input XORs with constant-bank operands.
+struct PhiloxKeys {
+    u32 k[20];
+};
+__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const PhiloxKeys &K) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        u32 n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+#ifdef MAPF_PHILOX_WIDE
+        u64 p0, p1;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(c0), "r"(0xD2511F53u));
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(c2), "r"(0xCD9E8D57u));
+        const u32 hi0 = (u32)(p0 >> 32), lo0 = (u32)p0, hi1 = (u32)(p1 >> 32), lo1 = (u32)p1;
+#else
+        const u32 hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const u32 hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#endif
+        const u32 n0 = hi1 ^ c1 ^ K.k[2 * r], n2 = hi0 ^ c3 ^ K.k[2 * r + 1];
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     Philox4 out;
     out.v[0] = c0; out.v[1] = c1; out.v[2] = c2; out.v[3] = c3;
@@ -182,50 +248,114 @@ __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3,
 // Counter layout of the sampling stream: (env low, env high, step low, step high<<8 | block); key = seed.
 // block b < 8 supplies the slip draws of agents 4b..4b+3 (one 32-bit word w each, u = w * 2**-32);
 // block 15 supplies the random-policy action (words 0,1 as a 64-bit fraction of nA).
-__device__ __forceinline__ Philox4 philox_block(u64 seed, u64 env, u64 step, u32 block) {
-    return philox4x32_10((u32)env, (u32)(env >> 32), (u32)step, ((u32)(step >> 32) << 8) | block, (u32)seed,
-                         (u32)(seed >> 32));
+__device__ __forceinline__ Philox4 philox_block(const PhiloxKeys &K, u64 env, u64 step, u32 block) {
+    return philox4x32_10((u32)env, (u32)(env >> 32), (u32)step, ((u32)(step >> 32) << 8) | block, K);
 }
 
-__device__ __forceinline__ double u32_to_uniform(u32 w) { return (double)w * 2.3283064365386963e-10; }  // 2**-32
+// ---- shared memory: small per-pattern tables + the move table ------------------------------------------------
+// Layout of the dynamic shared memory of every hot kernel (pattern tables have one 32-byte row per pattern):
+//   [0, 256)       thr    u32[8][8]
+//   [256, 512)     cum    f64[8][4]
+//   [512, 768)     pp     f64[8][4]
+//   [768, 1152)    reward f64[48]
+//   [1152, 1168)   mbarrier of the bulk copy
+//   [1168 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
+#define MAPF_SMEM_THR 0
+#define MAPF_SMEM_CUM 256
+#define MAPF_SMEM_PP 512
+#define MAPF_SMEM_REW 768
+#define MAPF_SMEM_BAR 1152
+#define MAPF_SMEM_LUT 1168
 
-// ---- shared-memory staging of the move table and the small constant tables -----------------------------------
+// Shared memory is addressed through 32-bit shared-window addresses and explicit ld.shared, so that every table
+// access is one LDS with an immediate offset (no generic-address arithmetic).
 struct SmemTables {
-    const u64 *lut;        // smem or global
-    const double *probtab; // smem [8]
-    const double *reward;  // smem [3*MAPF_REW_STRIDE]
+    u32 base;          // shared-window address of the dynamic shared memory
+    u32 lut;           // shared-window address of the staged move table
+    const u64 *lut_g;  // the move table in global memory
 };
 
-// Layout of the dynamic shared memory of every hot kernel: [probtab 8 f64][reward 48 f64][lut L*5 u64 (if staged)]
-#define MAPF_SMEM_SMALL_BYTES ((8 + 3 * MAPF_REW_STRIDE) * 8)
+__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 
+template <int OFF>
+__device__ __forceinline__ u64 lds_u64(u32 addr) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64(u32 addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint2 lds_u32x2(u32 addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// Start staging: the small tables are written by the CTA's threads, the move table is fetched by ONE bulk
+// asynchronous copy (cp.async.bulk, the TMA engine) that completes on an mbarrier; compute that does not need
+// the table (loads, state decode, Philox) overlaps with it.  Call tables_wait() before the first table access.
 template <bool LUTS>
-__device__ __forceinline__ SmemTables stage_tables(const DevSpec &sp, unsigned char *smem) {
-    double *pt = reinterpret_cast<double *>(smem);
-    double *rw = pt + 8;
-    u64 *lut_s = reinterpret_cast<u64 *>(smem + MAPF_SMEM_SMALL_BYTES);
-    for (int i = threadIdx.x; i < 8; i += blockDim.x) pt[i] = sp.probtab[i];
-    for (int i = threadIdx.x; i < 3 * MAPF_REW_STRIDE; i += blockDim.x) rw[i] = sp.reward[i];
-    SmemTables t;
-    t.probtab = pt;
-    t.reward = rw;
-    if (LUTS) {
-        const int n_ent = sp.L * 5;
-        // 128-bit copies of the table (global -> shared); the table base is 16-byte aligned
-        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(sp.lut);
-        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(lut_s);
-        for (int i = threadIdx.x; i < n_ent / 2; i += blockDim.x) dst[i] = __ldg(src + i);
-        if ((n_ent & 1) && threadIdx.x == 0) lut_s[n_ent - 1] = __ldg(sp.lut + n_ent - 1);
-        t.lut = lut_s;
-    } else {
-        t.lut = sp.lut;
+__device__ __forceinline__ SmemTables tables_begin(const DevSpec &sp, unsigned char *smem) {
+    u32 *thr = reinterpret_cast<u32 *>(smem + MAPF_SMEM_THR);
+    double *cum = reinterpret_cast<double *>(smem + MAPF_SMEM_CUM);
+    double *pp = reinterpret_cast<double *>(smem + MAPF_SMEM_PP);
+    double *rw = reinterpret_cast<double *>(smem + MAPF_SMEM_REW);
+    u64 *bar = reinterpret_cast<u64 *>(smem + MAPF_SMEM_BAR);
+    unsigned char *lut_s = smem + MAPF_SMEM_LUT;
+    if (LUTS && threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = threadIdx.x; i < MAPF_MAX_PATTERNS * 8; i += blockDim.x) thr[i] = (&sp.thr[0][0])[i];
+    for (int i = threadIdx.x; i < MAPF_MAX_PATTERNS * 4; i += blockDim.x) {
+        cum[i] = (&sp.cum[0][0])[i];
+        pp[i] = (&sp.pp[0][0])[i];
+    }
+    for (int i = threadIdx.x; i < 3 * MAPF_REW_STRIDE; i += blockDim.x) rw[i] = sp.reward[i];
     __syncthreads();
+    if (LUTS && threadIdx.x == 0) {
+        const u32 bytes = sp.lut_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        u32 off = 0;
+        while (off < bytes) {  // pieces of at most 32 KiB
+            const u32 piece = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(lut_s + off)),
+                         "l"(reinterpret_cast<const unsigned char *>(sp.lut) + off), "r"(piece), "r"(smem_u32(bar))
+                         : "memory");
+            off += piece;
+        }
+    }
+    SmemTables t;
+    t.base = smem_u32(smem);
+    t.lut = smem_u32(lut_s);
+    t.lut_g = sp.lut;
     return t;
 }
 
 template <bool LUTS>
-__device__ __forceinline__ u64 lut_get(const u64 *lut, int idx) {
-    if (LUTS) return lut[idx];
-    return __ldg(lut + idx);
+__device__ __forceinline__ void tables_wait(unsigned char *smem) {
+    if (LUTS) {
+        const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
+        u32 ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(0u)
+                         : "memory");
+        } while (!ok);
+    }
+}
+
+// move-table entry of (cell, action): `act8` is action * 8 (+ the table's shared-window address when staged)
+template <bool LUTS>
+__device__ __forceinline__ u64 lut_entry(const SmemTables &tb, u32 cell, u32 act8) {
+    if (LUTS) return lds_u64<0>(cell * 40u + act8);
+    return __ldg(reinterpret_cast<const u64 *>(reinterpret_cast<const unsigned char *>(tb.lut_g) + (cell * 40u + act8)));
 }

@@ -1,0 +1,21 @@
+// mapf_host.h -- glue between the per-agent-count kernel instantiation units (mapf_inst.cu, compiled once per N)
+// and the C ABI (mapf_capi.cu).
+#pragma once
+#include <cstddef>
+
+struct KernelSet {
+    const void *step_philox1 = nullptr;  // k_step<N, W, LUTS, TAPE=false, EPT=1>
+    const void *step_philox2 = nullptr;  // ... EPT=2 (128-bit I/O)
+    const void *step_tape = nullptr;     // k_step<N, W, LUTS, TAPE=true, EPT=1>
+    const void *rollout_philox = nullptr, *rollout_tape = nullptr;
+    const void *expand = nullptr, *expand_range = nullptr;
+    const void *count = nullptr, *count_range = nullptr;
+    const void *decode = nullptr, *encode = nullptr;
+    size_t expand_slab_bytes = 0;        // per warp
+};
+
+// words: 1 or 2; luts: move table staged in shared memory
+typedef void (*mapf_kernels_fn)(int words, int luts, KernelSet *out);
+#define DECL(N) void mapf_get_kernels_##N(int words, int luts, KernelSet *out);
+DECL(1) DECL(2) DECL(3) DECL(4) DECL(5) DECL(6) DECL(7) DECL(8) DECL(9) DECL(10) DECL(11) DECL(12) DECL(13)
+#undef DECL

@@ -1,0 +1,42 @@
+// mapf_inst.cu -- instantiates every hot kernel for ONE agent count (compile with -DMAPF_N=<n>); the Makefile
+// builds the 13 units in parallel.
+#include "mapf_host.h"
+#include "mapf_kernels.cuh"
+
+#ifndef MAPF_N
+#error "compile with -DMAPF_N=<agents>"
+#endif
+
+template <int N, int W, bool LUTS>
+static void fill(KernelSet *k) {
+    k->step_philox1 = (const void *)k_step<N, W, LUTS, false, 1>;
+    k->step_philox2 = (const void *)k_step<N, W, LUTS, false, 2>;
+    k->step_tape = (const void *)k_step<N, W, LUTS, true, 1>;
+    k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false>;
+    k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true>;
+    k->expand = (const void *)k_expand<N, W, LUTS, false>;
+    k->expand_range = (const void *)k_expand<N, W, LUTS, true>;
+    k->count = (const void *)k_count<N, W, false>;
+    k->count_range = (const void *)k_count<N, W, true>;
+    k->decode = (const void *)k_decode<N, W>;
+    k->encode = (const void *)k_encode<N, W>;
+    k->expand_slab_bytes = sizeof(ExpandSlab<N>);
+}
+
+#define CAT_(a, b) a##b
+#define CAT(a, b) CAT_(a, b)
+
+void CAT(mapf_get_kernels_, MAPF_N)(int words, int luts, KernelSet *out) {
+    // two-word states need L**n >= 2**63 with L <= 65535, i.e. at least 4 agents
+    if (words == 1) {
+        if (luts) fill<MAPF_N, 1, true>(out);
+        else fill<MAPF_N, 1, false>(out);
+    } else {
+#if MAPF_N >= 4
+        if (luts) fill<MAPF_N, 2, true>(out);
+        else fill<MAPF_N, 2, false>(out);
+#else
+        (void)out;
+#endif
+    }
+}

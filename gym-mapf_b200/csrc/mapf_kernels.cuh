@@ -2,7 +2,8 @@
 //
 // Mapping ("T" family): one thread per emitted unit -- one env-step in step/rollout mode, one P[s][a] record in
 // expand mode.  All per-agent loops are unrolled over the template parameter N, so an agent's cell, move-table
-// entry and outcome digit live in registers.  The per-(cell, action) move table is staged in shared memory.
+// entry and outcome digit live in registers.  The per-(cell, action) move table is staged in shared memory by one
+// bulk asynchronous copy (TMA engine) per CTA.
 //
 // Reference citations are file:line relative to /root/reference/gym_mapf/envs/.
 #pragma once
@@ -47,9 +48,17 @@ __device__ __forceinline__ void bm_move(const BitmapView &bm, int r, int c, int 
     nc = ok ? tc : c;
 }
 
+// The merge patterns that can occur, as 9-bit triples (mask of slot 0 | mask of slot 1 << 3 | mask of slot 2 << 6)
+// of candidate bits {intended = 1, right = 2, left = 4}; the index of a triple is its pattern id.
+struct PatternList {
+    u32 triple[MAPF_MAX_PATTERNS];
+    int count;
+};
+
 // single_agent_movements (mapf_env.py:163-184) for one (cell, action): candidates [intended, right, left],
 // zero-probability candidates dropped (cand_mask), equal destinations merged into the first occurrence.
-__device__ __forceinline__ u64 bm_entry(const BitmapView &bm, int r, int c, int a, int cand_mask) {
+__device__ __forceinline__ u64 bm_entry(const BitmapView &bm, int r, int c, int a, int cand_mask,
+                                        const PatternList &pats) {
     // POSSIBILITIES (__init__.py:19-25): right/left slip of STAY,UP,RIGHT,DOWN,LEFT
     const int slip_r[5] = {0, 2, 3, 4, 1};
     const int slip_l[5] = {0, 4, 1, 2, 3};
@@ -68,12 +77,15 @@ __device__ __forceinline__ u64 bm_entry(const BitmapView &bm, int r, int c, int 
         else { dest[k] = id; mask[k] = 1u << j; ++k; }
     }
     for (int q = k; q < 3; ++q) dest[q] = dest[0];
-    return (u64)dest[0] | ((u64)dest[1] << 16) | ((u64)dest[2] << 32) | ((u64)mask[0] << 48) | ((u64)mask[1] << 51) |
-           ((u64)mask[2] << 54) | ((u64)k << 57);
+    const u32 triple = mask[0] | (mask[1] << 3) | (mask[2] << 6);
+    u32 pid = 0;
+    for (int q = 0; q < pats.count; ++q)
+        if (pats.triple[q] == triple) pid = (u32)q;
+    return (u64)dest[0] | ((u64)dest[1] << 16) | ((u64)dest[2] << 32) | ((u64)(pid * 32u) << 48) | ((u64)k << 56);
 }
 
-__global__ void k_build_moves(const u32 *__restrict__ colbits, const u32 *__restrict__ colbase, int H, int W, int wpc,
-                              int cand_mask, u64 *__restrict__ lut, u32 *__restrict__ cell_rc) {
+static __global__ void k_build_moves(const u32 *__restrict__ colbits, const u32 *__restrict__ colbase, int H, int W, int wpc,
+                              int cand_mask, PatternList pats, u64 *__restrict__ lut, u32 *__restrict__ cell_rc) {
     extern __shared__ u32 bm_smem[];
     u32 *s_bits = bm_smem;
     u32 *s_base = bm_smem + W * wpc;
@@ -86,50 +98,52 @@ __global__ void k_build_moves(const u32 *__restrict__ colbits, const u32 *__rest
         if (!bm_free(bm, r, c)) continue;
         int id = bm_rank(bm, r, c);
         cell_rc[id] = ((u32)r << 16) | (u32)c;
-        for (int a = 0; a < 5; ++a) lut[id * 5 + a] = bm_entry(bm, r, c, a, cand_mask);
+        for (int a = 0; a < 5; ++a) lut[id * 5 + a] = bm_entry(bm, r, c, a, cand_mask, pats);
     }
 }
 
 // =====================================================================================================
 // Bulk state <-> cells (state_to_locations / locations_to_state, mapf_env.py:358-371)
 // =====================================================================================================
-__device__ __forceinline__ void load_state(const DevSpec &sp, const u64 *states, i64 b, u64 &lo, u64 &hi) {
-    if (sp.words == 1) { lo = states[b]; hi = 0; }
+template <int WORDS>
+__device__ __forceinline__ void load_state(const u64 *states, i64 b, u64 &lo, u64 &hi) {
+    if (WORDS == 1) { lo = states[b]; hi = 0; }
     else { ulonglong2 v = reinterpret_cast<const ulonglong2 *>(states)[b]; lo = v.x; hi = v.y; }
 }
-__device__ __forceinline__ void store_state(const DevSpec &sp, u64 *states, i64 b, u64 lo, u64 hi) {
-    if (sp.words == 1) states[b] = lo;
+template <int WORDS>
+__device__ __forceinline__ void store_state(u64 *states, i64 b, u64 lo, u64 hi) {
+    if (WORDS == 1) states[b] = lo;
     else reinterpret_cast<ulonglong2 *>(states)[b] = make_ulonglong2(lo, hi);
 }
 
-template <int N>
+template <int N, int WORDS>
 __global__ void __launch_bounds__(256) k_decode(DevSpec sp, const u64 *__restrict__ states, i64 B, int *__restrict__ cells) {
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
         u64 lo, hi;
-        load_state(sp, states, b, lo, hi);
+        load_state<WORDS>(states, b, lo, hi);
         int cell[N];
-        decode_state<N>(sp, lo, hi, cell);
+        decode_state<N, WORDS>(sp, lo, hi, cell);
 #pragma unroll
         for (int i = 0; i < N; ++i) cells[b * N + i] = cell[i];
     }
 }
 
-template <int N>
+template <int N, int WORDS>
 __global__ void __launch_bounds__(256) k_encode(DevSpec sp, const int *__restrict__ cells, i64 B, u64 *__restrict__ states) {
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
         int cell[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) cell[i] = cells[b * N + i];
+        for (int i = 0; i < N; ++i) cell[i] = min(max(cells[b * N + i], 0), sp.L - 1);
         u64 lo, hi;
-        encode_state<N>(sp, cell, lo, hi);
-        store_state(sp, states, b, lo, hi);
+        encode_state<N, WORDS>(sp, cell, lo, hi);
+        store_state<WORDS>(states, b, lo, hi);
     }
 }
 
 // =====================================================================================================
 // Row sources: explicit (state, action) pairs, or a slab of the full table generated from the row index
 // =====================================================================================================
-template <bool RANGE>
+template <int WORDS, bool RANGE>
 __device__ __forceinline__ void row_input(const DevSpec &sp, const u64 *states, const int *actions, u64 sb_lo, u64 sb_hi,
                                           i64 b, u64 &lo, u64 &hi, u32 &a) {
     if (RANGE) {
@@ -138,21 +152,21 @@ __device__ __forceinline__ void row_input(const DevSpec &sp, const u64 *states, 
         lo = sb_lo + off;
         hi = sb_hi + (lo < sb_lo ? 1ull : 0ull);
     } else {
-        load_state(sp, states, b, lo, hi);
+        load_state<WORDS>(states, b, lo, hi);
         a = (u32)actions[b];
     }
 }
 
 // len(P[s][a]) (mapf_env.py:448-479): 1 for a terminal state, else the product of merged-outcome counts
-template <int N, bool RANGE>
+template <int N, int WORDS, bool RANGE>
 __global__ void __launch_bounds__(256) k_count(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions,
                                                u64 sb_lo, u64 sb_hi, i64 B, i64 *__restrict__ row_len) {
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
         u64 lo, hi;
         u32 a;
-        row_input<RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
+        row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
         int cell[N], act[N];
-        decode_state<N>(sp, lo, hi, cell);
+        decode_state<N, WORDS>(sp, lo, hi, cell);
         decode_action<N>(a, act);
         i64 len = 1;
         if (!is_terminal<N>(sp, cell)) {
@@ -193,7 +207,7 @@ __device__ __forceinline__ i64 block_scan_256(i64 v, i64 *warp_sums, i64 &block_
     return incl - v;  // exclusive
 }
 
-__global__ void __launch_bounds__(256) k_scan_partials(const i64 *__restrict__ in, i64 B, i64 *__restrict__ partial) {
+static __global__ void __launch_bounds__(256) k_scan_partials(const i64 *__restrict__ in, i64 B, i64 *__restrict__ partial) {
     __shared__ i64 ws[8];
     i64 base = (i64)blockIdx.x * SCAN_CHUNK;
     i64 s = 0;
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(256) k_scan_partials(const i64 *__restrict__ i
 }
 
 // single block: exclusive scan of the per-chunk totals in place; partial[n_chunks] = grand total
-__global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_chunks) {
+static __global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_chunks) {
     __shared__ i64 ws[8];
     i64 carry = 0;
     for (i64 base = 0; base < n_chunks; base += 256) {
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_chunks) 
     if (threadIdx.x == 0) partial[n_chunks] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict__ in, i64 B, const i64 *__restrict__ partial,
+static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict__ in, i64 B, const i64 *__restrict__ partial,
                                                     i64 *__restrict__ row_ptr) {
     __shared__ i64 ws[8];
     i64 base = (i64)blockIdx.x * SCAN_CHUNK;
@@ -261,39 +275,43 @@ struct ExpandSlab {
     u64 ent[N][32];   // move-table entry of agent i for row r
     u64 st[2][32];    // the row's own state (terminal rows re-emit it)
     u32 pref[33];     // exclusive scan of the 32 row lengths
+    u32 pad;
     u16 prev[N][32];  // current cell of agent i
     u8 parked[32];    // SoC: agents parked on their goal choosing STAY
     u8 term[32];
 };
 
-template <int N, bool LUTS, bool RANGE>
+template <int N, int WORDS, bool LUTS, bool RANGE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
 k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
          const i64 *__restrict__ row_ptr, u64 *__restrict__ next_state, double *__restrict__ prob,
          double *__restrict__ reward, u8 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemTables tb = stage_tables<LUTS>(sp, smem);
-    const int lut_bytes = LUTS ? ((sp.L * 5 * 8 + 15) & ~15) : 0;
+    SmemTables tb = tables_begin<LUTS>(sp, smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_SMALL_BYTES + lut_bytes)[wid];
+    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
     const i64 n_batches = (B + 31) >> 5;
     const i64 warps_total = (i64)gridDim.x * (blockDim.x >> 5);
+    bool ready = false;
     for (i64 batch = (i64)blockIdx.x * (blockDim.x >> 5) + wid; batch < n_batches; batch += warps_total) {
         // ---------------- phase A
         const i64 b = batch * 32 + lane;
         u32 len = 0;
+        int cell[N], act[N];
+        u64 lo = 0, hi = 0;
         if (b < B) {
-            u64 lo, hi;
             u32 a;
-            row_input<RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
-            int cell[N], act[N];
-            decode_state<N>(sp, lo, hi, cell);
+            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
+            decode_state<N, WORDS>(sp, lo, hi, cell);
             decode_action<N>(a, act);
+        }
+        if (!ready) { tables_wait<LUTS>(smem); ready = true; }
+        if (b < B) {
             const bool term = is_terminal<N>(sp, cell);
             len = 1;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                u64 e = lut_get<LUTS>(tb.lut, cell[i] * 5 + act[i]);
+                u64 e = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
                 sl.ent[i][lane] = e;
                 sl.prev[i][lane] = (u16)cell[i];
                 len *= ENT_K(e);
@@ -322,8 +340,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             u32 o = j - sl.pref[r];
             const i64 idx = out0 + j;
             if (sl.term[r]) {  // [((1.0, False), s, 0, True)]  (mapf_env.py:455-456)
-                if (sp.words == 1) next_state[idx] = sl.st[0][r];
-                else reinterpret_cast<ulonglong2 *>(next_state)[idx] = make_ulonglong2(sl.st[0][r], sl.st[1][r]);
+                store_state<WORDS>(next_state, idx, sl.st[0][r], sl.st[1][r]);
                 prob[idx] = 1.0;
                 reward[idx] = 0.0;
                 flags[idx] = 1;
@@ -331,7 +348,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             }
             // outcome digits: itertools.product, the LAST agent's digit moves fastest (mapf_env.py:467)
             int nxt[N], prv[N];
-            u32 pm[N];
+            u32 pj[N];
 #pragma unroll
             for (int i = N - 1; i >= 0; --i) {
                 const u64 e = sl.ent[i][r];
@@ -340,14 +357,14 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
                 if (k == 1) { d = 0; }
                 else if (k == 2) { d = o & 1u; o >>= 1; }
                 else { u32 q = __umulhi(o, 0xAAAAAAABu) >> 1; d = o - 3u * q; o = q; }
-                nxt[i] = (int)((u32)(e >> (16 * d)) & 0xffffu);
-                pm[i] = (u32)(e >> (48 + 3 * d)) & 7u;
+                nxt[i] = (int)ent_dest(e, d);
+                pj[i] = ENT_POFF(e) + d * 8u;
                 prv[i] = (int)sl.prev[i][r];
             }
             // probability: left-to-right product (mapf_env.py:468)
-            double p = tb.probtab[pm[0]];
+            double p = lds_f64<MAPF_SMEM_PP>(tb.base + pj[0]);
 #pragma unroll
-            for (int i = 1; i < N; ++i) p = __dmul_rn(p, tb.probtab[pm[i]]);
+            for (int i = 1; i < N; ++i) p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + pj[i]));
             // reward / done / collision (mapf_env.py:225-235): clash beats goal
             const bool clash = has_clash<N>(prv, nxt);
             bool goal = true;
@@ -355,21 +372,21 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             for (int i = 0; i < N; ++i) goal = goal && (nxt[i] == (int)sp.goal[i]);
             const int kind = clash ? 1 : (goal ? 2 : 0);
             u64 nlo, nhi;
-            encode_state<N>(sp, nxt, nlo, nhi);
-            if (sp.words == 1) next_state[idx] = nlo;
-            else reinterpret_cast<ulonglong2 *>(next_state)[idx] = make_ulonglong2(nlo, nhi);
+            encode_state<N, WORDS>(sp, nxt, nlo, nhi);
+            store_state<WORDS>(next_state, idx, nlo, nhi);
             prob[idx] = p;
-            reward[idx] = tb.reward[kind * MAPF_REW_STRIDE + sl.parked[r]];
+            reward[idx] = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[r]) * 8u);
             flags[idx] = (u8)((kind != 0 ? 1 : 0) | (clash ? 2 : 0));
         }
         __syncwarp();
     }
+    if (!ready) tables_wait<LUTS>(smem);  // never leave a CTA while its bulk copy is in flight
 }
 
 // =====================================================================================================
 // Checksums of a record array (mod 2**64), accumulated into out8 with atomics
 // =====================================================================================================
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_checksum(int words, i64 n, i64 index_base, const u64 *__restrict__ next_state, const double *__restrict__ prob,
            const double *__restrict__ reward, const u8 *__restrict__ flags, u64 *out8) {
     u64 acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -396,152 +413,186 @@ k_checksum(int words, i64 n, i64 index_base, const u64 *__restrict__ next_state,
 // =====================================================================================================
 // Step / rollout (MapfEnv.step, mapf_env.py:237-266)
 // =====================================================================================================
-struct StepOut {
+// Everything about one env that does not need the move table: its decoded cells, action digits and draws.
+template <int N>
+struct EnvIn {
+    int cell[N];
+    int act[N];
+    u32 w[((N + 3) / 4) * 4];  // Philox words, one per agent
+    u64 lo, hi;
+};
+
+struct EnvOut {
     u64 lo, hi;
     double reward, prob;
     u32 done, coll;
 };
 
-// One env-step with the cells already decoded.  `draw(i)` supplies agent i's uniform.
-template <int N, bool LUTS, class Draw>
-__device__ __forceinline__ void step_cells(const DevSpec &sp, const SmemTables &tb, int (&cell)[N], u32 a, Draw draw,
-                                           double &reward, double &prob, u32 &done, u32 &coll, bool &terminal) {
-    terminal = is_terminal<N>(sp, cell);
-    if (terminal) {  // (s, 0, True, {"prob": 0})  (mapf_env.py:238-240); no draw is consumed
-        reward = 0.0; prob = 0.0; done = 1; coll = 0;
-        return;
+template <int N>
+__device__ __forceinline__ void env_draws(const PhiloxKeys &K, u64 env, u64 step, EnvIn<N> &in) {
+#pragma unroll
+    for (int b = 0; b < (N + 3) / 4; ++b) {
+        Philox4 x = philox_block(K, env, step, (u32)b);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) in.w[b * 4 + q] = x.v[q];
     }
-    int act[N], nxt[N];
-    decode_action<N>(a, act);
-    double total = 1.0;
+}
+
+// One sampled joint transition.  TAPE: agent i's uniform is u[i] (a replayed reference draw) and the choice is
+// `(cumsum > u).argmax()` in fp64 (mapf_env.py:255).  Otherwise the draw is the 32-bit Philox word w, u = w * 2**-32,
+// and the same comparison is made on integers: cumsum_j > u  <=>  w <= thr_j.  The host guarantees that the last
+// threshold of every pattern is 2**32 - 1 (the probabilities of a pattern add up to 1), so the index is simply the
+// number of thresholds below w.
+template <int N, int WORDS, bool LUTS, bool TAPE>
+__device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &tb, const EnvIn<N> &in,
+                                           const double *__restrict__ u, u32 opts, int (&nxt)[N]) {
+    double total;
+    const bool term = is_terminal<N>(sp, in.cell);
+    const u32 act_base = LUTS ? tb.lut : 0u;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const u64 e = lut_get<LUTS>(tb.lut, cell[i] * 5 + act[i]);
-        const u32 k = ENT_K(e);
-        const double u = draw(i);
-        // categorical_sample: first index whose cumulative sum exceeds u, else 0 (mapf_env.py:255)
-        const double c0 = tb.probtab[ENT_MASK(e, 0)];
-        u32 pick = 0;
-        if (k >= 2 && !(c0 > u)) {
-            const double c1 = __dadd_rn(c0, tb.probtab[ENT_MASK(e, 1)]);
-            if (c1 > u) pick = 1;
-            else if (k >= 3) {
-                const double c2 = __dadd_rn(c1, tb.probtab[ENT_MASK(e, 2)]);
-                if (c2 > u) pick = 2;
-            }
+        const u64 e = lut_entry<LUTS>(tb, (u32)in.cell[i], (u32)in.act[i] * 8u + act_base);
+        const u32 row = tb.base + ENT_POFF(e);
+        u32 pick;
+        if (TAPE) {
+            const double ui = u[i];
+            const double c0 = lds_f64<MAPF_SMEM_CUM>(row), c1 = lds_f64<MAPF_SMEM_CUM + 8>(row),
+                         c2 = lds_f64<MAPF_SMEM_CUM + 16>(row);
+            pick = c0 > ui ? 0u : (c1 > ui ? 1u : (c2 > ui ? 2u : 0u));
+        } else {
+            const uint2 t = lds_u32x2<MAPF_SMEM_THR>(row);
+            const u32 w = in.w[i];
+            pick = (w > t.x ? 1u : 0u) + (w > t.y ? 1u : 0u);
         }
-        nxt[i] = (int)((u32)(e >> (16 * pick)) & 0xffffu);
-        total = __dmul_rn(total, tb.probtab[(u32)(e >> (48 + 3 * pick)) & 7u]);  // mapf_env.py:257
+        nxt[i] = (int)ent_dest(e, pick);
+        const double pi = lds_f64<MAPF_SMEM_PP>(row + pick * 8u);
+        total = i == 0 ? pi : __dmul_rn(total, pi);  // 1 * p0 * p1 * ... (mapf_env.py:250,257)
     }
-    const bool clash = has_clash<N>(cell, nxt);
+    const bool clash = has_clash<N>(in.cell, nxt);
     bool goal = true;
 #pragma unroll
     for (int i = 0; i < N; ++i) goal = goal && (nxt[i] == (int)sp.goal[i]);
     const int kind = clash ? 1 : (goal ? 2 : 0);
-    reward = tb.reward[kind * MAPF_REW_STRIDE + parked_agents<N>(sp, cell, act)];
-    prob = total;
-    done = kind != 0 ? 1 : 0;
-    coll = clash ? 1 : 0;
+    EnvOut out;
+    out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + parked_agents<N>(sp, in.cell, in.act)) * 8u);
+    out.prob = total;
+    out.done = kind != 0 ? 1u : 0u;
+    out.coll = clash ? 1u : 0u;
+    encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
+    if (term) {  // (s, 0, True, {"prob": 0})  (mapf_env.py:238-240): a no-op that consumes no draw
+        out.lo = in.lo; out.hi = in.hi; out.reward = 0.0; out.prob = 0.0; out.done = 1u; out.coll = 0u;
 #pragma unroll
-    for (int i = 0; i < N; ++i) cell[i] = nxt[i];
+        for (int i = 0; i < N; ++i) nxt[i] = in.cell[i];
+    }
+    if ((opts & 1u) && out.done) {  // MAPF_OPT_AUTO_RESET
+        out.lo = sp.s0[0]; out.hi = sp.s0[1];
+#pragma unroll
+        for (int i = 0; i < N; ++i) nxt[i] = (int)sp.start[i];
+    }
+    return out;
 }
 
-template <int N>
-struct PhiloxDraw {
-    u32 w[((N + 3) / 4) * 4];
-    __device__ __forceinline__ PhiloxDraw(u64 seed, u64 env, u64 step) {
-#pragma unroll
-        for (int b = 0; b < (N + 3) / 4; ++b) {
-            Philox4 x = philox_block(seed, env, step, (u32)b);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) w[b * 4 + q] = x.v[q];
-        }
-    }
-    __device__ __forceinline__ double operator()(int i) const { return u32_to_uniform(w[i]); }
-};
-
-struct TapeDraw {
-    const double *u;
-    __device__ __forceinline__ double operator()(int i) const { return u[i]; }
-};
-
-__device__ __forceinline__ u32 random_action(const DevSpec &sp, u64 seed, u64 env, u64 step) {
-    Philox4 x = philox_block(seed, env, step, 15u);
+__device__ __forceinline__ u32 random_action(const DevSpec &sp, const PhiloxKeys &K, u64 env, u64 step) {
+    Philox4 x = philox_block(K, env, step, 15u);
     return (u32)__umul64hi(((u64)x.v[0] << 32) | x.v[1], sp.nA);
 }
 
-template <int N, bool LUTS>
+// EPT = envs per thread per iteration.  EPT == 2 uses 128-bit loads/stores for the 8-byte fields (and 16-bit
+// stores for the two flag bytes); the launcher picks it only when B is even and every pointer is 16-byte aligned.
+// B < 2**31 (the launcher splits larger batches), so every index is 32-bit and an address is one wide multiply-add.
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
-k_step(DevSpec sp, const u64 *states, const int *__restrict__ actions, i64 B, const double *__restrict__ uniforms,
-       u64 seed, u64 step, u64 env0, u32 opts, u64 *next_states, double *__restrict__ reward, double *__restrict__ prob,
-       u8 *__restrict__ done, u8 *__restrict__ coll) {
+k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
+       const double *__restrict__ uniforms, u64 step, u64 env0, u32 opts, u64 *next_states,
+       double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemTables tb = stage_tables<LUTS>(sp, smem);
-    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
-        u64 lo, hi;
-        load_state(sp, states, b, lo, hi);
-        const u32 a = (u32)actions[b];
-        int cell[N];
-        decode_state<N>(sp, lo, hi, cell);
-        double r, p;
-        u32 d, c;
-        bool term;
-        if (uniforms) {
-            TapeDraw draw = {uniforms + b * N};
-            step_cells<N, LUTS>(sp, tb, cell, a, draw, r, p, d, c, term);
+    SmemTables tb = tables_begin<LUTS>(sp, smem);
+    bool ready = false;
+    const u32 n_items = B / EPT;
+    for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        EnvIn<N> in[EPT];
+        const u32 b = it * EPT;
+        if (EPT == 2 && WORDS == 1) {
+            const ulonglong2 s2 = reinterpret_cast<const ulonglong2 *>(states)[it];
+            const int2 a2 = reinterpret_cast<const int2 *>(actions)[it];
+            in[0].lo = s2.x; in[0].hi = 0; in[EPT - 1].lo = s2.y; in[EPT - 1].hi = 0;
+            decode_action<N>((u32)a2.x, in[0].act);
+            decode_action<N>((u32)a2.y, in[EPT - 1].act);
         } else {
-            // the draws are generated even for a terminal env (they are simply not used)
-            PhiloxDraw<N> draw(seed, env0 + (u64)b, step);
-            step_cells<N, LUTS>(sp, tb, cell, a, draw, r, p, d, c, term);
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) {
+                load_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
+                decode_action<N>((u32)actions[b + q], in[q].act);
+            }
         }
-        if (!term) encode_state<N>(sp, cell, lo, hi);
-        if ((opts & 1u) && d) { lo = sp.s0[0]; hi = sp.s0[1]; }  // MAPF_OPT_AUTO_RESET
-        store_state(sp, next_states, b, lo, hi);
-        reward[b] = r;
-        prob[b] = p;
-        done[b] = (u8)d;
-        coll[b] = (u8)c;
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            decode_state<N, WORDS>(sp, in[q].lo, in[q].hi, in[q].cell);
+            if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step, in[q]);
+        }
+        if (!ready) { tables_wait<LUTS>(smem); ready = true; }
+        EnvOut o[EPT];
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            int nxt[N];
+            o[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (size_t)(b + q) * N : nullptr, opts,
+                                                  nxt);
+        }
+        if (EPT == 2) {
+            if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
+            else {
+                store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
+                store_state<WORDS>(next_states, b + 1, o[EPT - 1].lo, o[EPT - 1].hi);
+            }
+            reinterpret_cast<double2 *>(reward)[it] = make_double2(o[0].reward, o[EPT - 1].reward);
+            reinterpret_cast<double2 *>(prob)[it] = make_double2(o[0].prob, o[EPT - 1].prob);
+            reinterpret_cast<u16 *>(done)[it] = (u16)(o[0].done | (o[EPT - 1].done << 8));
+            reinterpret_cast<u16 *>(coll)[it] = (u16)(o[0].coll | (o[EPT - 1].coll << 8));
+        } else {
+            store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
+            reward[b] = o[0].reward;
+            prob[b] = o[0].prob;
+            done[b] = (u8)o[0].done;
+            coll[b] = (u8)o[0].coll;
+        }
     }
+    if (!ready) tables_wait<LUTS>(smem);
 }
 
 // T steps per launch; the env's cells stay in registers between steps, each step's results go to slab t.
-template <int N, bool LUTS>
+template <int N, int WORDS, bool LUTS, bool TAPE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
-k_rollout(DevSpec sp, u64 *states, const int *__restrict__ actions, i64 T, i64 B, const double *__restrict__ uniforms,
-          u64 seed, u64 step0, u64 env0, u32 opts, u64 *__restrict__ next_states, double *__restrict__ reward,
-          double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
+k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ actions, i64 T, u32 B,
+          const double *__restrict__ uniforms, u64 step0, u64 env0, u32 opts, u64 *__restrict__ next_states,
+          double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemTables tb = stage_tables<LUTS>(sp, smem);
-    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
-        u64 lo, hi;
-        load_state(sp, states, b, lo, hi);
-        int cell[N];
-        decode_state<N>(sp, lo, hi, cell);
+    SmemTables tb = tables_begin<LUTS>(sp, smem);
+    bool ready = false;
+    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        EnvIn<N> in;
+        load_state<WORDS>(states, b, in.lo, in.hi);
+        decode_state<N, WORDS>(sp, in.lo, in.hi, in.cell);
         for (i64 t = 0; t < T; ++t) {
-            const i64 o = t * B + b;
-            const u32 a = actions ? (u32)actions[o] : random_action(sp, seed, env0 + (u64)b, step0 + (u64)t);
-            double r, p;
-            u32 d, c;
-            bool term;
-            if (uniforms) {
-                TapeDraw draw = {uniforms + o * N};
-                step_cells<N, LUTS>(sp, tb, cell, a, draw, r, p, d, c, term);
-            } else {
-                PhiloxDraw<N> draw(seed, env0 + (u64)b, step0 + (u64)t);
-                step_cells<N, LUTS>(sp, tb, cell, a, draw, r, p, d, c, term);
-            }
-            if (!term) encode_state<N>(sp, cell, lo, hi);
-            if ((opts & 1u) && d) {
-                lo = sp.s0[0]; hi = sp.s0[1];
+            const i64 o = t * (i64)B + b;
+            const u64 env = env0 + (u64)b, stp = step0 + (u64)t;
+            const u32 a = actions ? (u32)actions[o] : random_action(sp, keys, env, stp);
+            decode_action<N>(a, in.act);
+            if (!TAPE) env_draws<N>(keys, env, stp, in);
+            if (!ready) { tables_wait<LUTS>(smem); ready = true; }
+            int nxt[N];
+            EnvOut r = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in, TAPE ? uniforms + o * N : nullptr, opts, nxt);
+            store_state<WORDS>(next_states, o, r.lo, r.hi);
+            reward[o] = r.reward;
+            prob[o] = r.prob;
+            done[o] = (u8)r.done;
+            coll[o] = (u8)r.coll;
+            // carry the env forward in registers (cells of the possibly reset next state)
+            in.lo = r.lo;
+            in.hi = r.hi;
 #pragma unroll
-                for (int i = 0; i < N; ++i) cell[i] = (int)sp.start[i];
-            }
-            store_state(sp, next_states, o, lo, hi);
-            reward[o] = r;
-            prob[o] = p;
-            done[o] = (u8)d;
-            coll[o] = (u8)c;
+            for (int i = 0; i < N; ++i) in.cell[i] = nxt[i];
         }
-        store_state(sp, states, b, lo, hi);
+        store_state<WORDS>(states, b, in.lo, in.hi);
     }
+    if (!ready) tables_wait<LUTS>(smem);
 }
