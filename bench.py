@@ -241,6 +241,22 @@ def run_ours(args):
         one_step(i)
     barrier()
 
+    # The K steps of one repetition are captured once into a CUDA graph (K kernel nodes joined by programmatic
+    # dependent-launch edges) and replayed: the host launch path (~13 us per call through Python/ctypes) would
+    # otherwise be as long as the kernel itself.  --no-graph times plain stream launches instead.
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            one_step(0)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(K):
+                one_step(i)
+        barrier()
+
     # ---- timed region: exactly K steps per repetition, CUDA events on the launching stream; repetitions until the
     # GPU has been busy long enough for nvidia-smi to sample clocks under load.  The median repetition is reported.
     sampler = ClockSampler(local)
@@ -252,8 +268,11 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(K):
-            one_step(i)
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                one_step(i)
         e1.record()
         barrier()
         reps_ms.append(e0.elapsed_time(e1))
@@ -321,6 +340,8 @@ def run_ours(args):
                              "kernel": "k_step<4,smem move table>", "bytes_per_unit": STEP_BYTES,
                              "units_per_launch": B},
                 "e2e": e2e, "gpu_launches": K, "clocks": clocks,
+                "launch": ("one CUDA graph of K step kernels (programmatic dependent launch)" if graph is not None
+                           else "K stream launches"),
                 "shard_checksums": {"keys": ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi",
                                              "sum_prob_bits", "sum_reward_bits", "ordered"], "per_gpu": shard_sums}}
         if world == 1 and not args.no_cpu:
@@ -343,6 +364,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=1.5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -271,6 +271,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         mul *= (u128)L;
     }
     sp.s0[0] = (u64)s0; sp.s0[1] = (u64)(s0 >> 64);
+    sp.sgoal[0] = (u64)sg; sp.sgoal[1] = (u64)(sg >> 64);
 
     // ---- probabilities in the reference's order (mapf_env.py:131-132,168-170,177-179)
     const double rf = spec->fail_prob / 2, lf = spec->fail_prob / 2;
@@ -649,7 +650,30 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             fn = ctx->ks.step_philox1;
             grid = grid_for(nb, ctx->threads, ctx->grid_step1);
         }
-        LAUNCH(fn, grid, ctx->threads, ctx->smem_base, stream, args);
+        static int use_pdl = -1;
+        if (use_pdl < 0) {
+            const char *e = getenv("MAPF_PDL");
+            use_pdl = e ? atoi(e) : 1;
+        }
+        if (use_pdl) {
+            // programmatic stream serialization: this launch may begin (up to its griddepcontrol.wait) while the
+            // previous kernel of the stream is still draining
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(grid);
+            cfg.blockDim = dim3(ctx->threads);
+            cfg.dynamicSmemBytes = ctx->smem_base;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+            if (e != cudaSuccess) return fail(MAPF_ERR_CUDA, "launch k_step: %s", cudaGetErrorString(e));
+        } else {
+            LAUNCH(fn, grid, ctx->threads, ctx->smem_base, stream, args);
+        }
     }
     return MAPF_OK;
 }

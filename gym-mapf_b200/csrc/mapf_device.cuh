@@ -62,6 +62,7 @@ struct DevSpec {
     FastDiv divLL;     // division by L*L
     Div32 divL;        // division by L of a two-digit chunk
     u64 s0[2];         // start state
+    u64 sgoal[2];      // locations_to_state(agents_goals)
     const u64 *lut;    // [L*5] move table, global memory
     u16 goal[16];      // goal cell per agent (mapf_env.py:158)
     u16 start[16];
@@ -173,17 +174,16 @@ __device__ __forceinline__ void decode_action(u32 a, int (&act)[N]) {
     }
 }
 
-// is_terminal (mapf_env.py:210-223): two agents on one cell, or every agent on its own goal
+// is_terminal (mapf_env.py:210-223): two agents on one cell, or every agent on its own goal (the state IS the goal
+// state: one 64/128-bit compare instead of one compare per agent)
 template <int N>
-__device__ __forceinline__ bool is_terminal(const DevSpec &sp, const int (&cell)[N]) {
-    bool dup = false, all_goal = true;
+__device__ __forceinline__ bool is_terminal(const DevSpec &sp, const int (&cell)[N], u64 lo, u64 hi) {
+    bool dup = false;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        all_goal = all_goal && (cell[i] == (int)sp.goal[i]);
+    for (int i = 0; i < N; ++i)
 #pragma unroll
         for (int j = i + 1; j < N; ++j) dup = dup || (cell[i] == cell[j]);
-    }
-    return dup || all_goal;
+    return dup || (lo == sp.sgoal[0] && hi == sp.sgoal[1]);
 }
 
 // _is_collision_transition_from_local_states (mapf_env.py:378-389): swap or vertex conflict over all pairs.
@@ -205,15 +205,24 @@ __device__ __forceinline__ bool has_clash(const int (&prev)[N], const int (&nxt)
     return c;
 }
 
-// number of agents parked on their goal that chose STAY (mapf_env.py:441-446); 0 under Makespan
+// number of agents parked on their goal that chose STAY (mapf_env.py:441-446); 0 under Makespan.
+// (prev ^ goal) | act is zero exactly for such an agent.
 template <int N>
 __device__ __forceinline__ int parked_agents(const DevSpec &sp, const int (&prev)[N], const int (&act)[N]) {
     int k = 0;
     if (sp.soc) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) k += (prev[i] == (int)sp.goal[i] && act[i] == 0) ? 1 : 0;
+        for (int i = 0; i < N; ++i) k += ((((u32)prev[i] ^ (u32)sp.goal[i]) | (u32)act[i]) == 0u) ? 1 : 0;
     }
     return k;
+}
+
+// (w > a) + (w > b) with the carry flag: two borrow-generating subtractions
+__device__ __forceinline__ u32 count_below(u32 w, u32 a, u32 b) {
+    u32 t, n;
+    asm("{\n\t.reg .u32 t0;\n\tsub.cc.u32 t0, %2, %1;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(t) : "r"(w), "r"(a));
+    asm("{\n\t.reg .u32 t0;\n\tsub.cc.u32 t0, %2, %1;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(n) : "r"(w), "r"(b), "r"(t));
+    return n;
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the device-side sampling mode -------
@@ -228,7 +237,7 @@ struct PhiloxKeys {
 __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const PhiloxKeys &K) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-#ifdef MAPF_PHILOX_WIDE
+#ifndef MAPF_PHILOX_NARROW  // one wide multiply per product (measured faster than separate hi/lo multiplies)
         u64 p0, p1;
         asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(c0), "r"(0xD2511F53u));
         asm("mul.wide.u32 %0, %1, %2;" : "=l"(p1) : "r"(c2), "r"(0xCD9E8D57u));
@@ -334,6 +343,7 @@ __device__ __forceinline__ SmemTables tables_begin(const DevSpec &sp, unsigned c
     SmemTables t;
     t.base = smem_u32(smem);
     t.lut = smem_u32(lut_s);
+    asm volatile("" : "+r"(t.base), "+r"(t.lut));  // opaque: keep both in registers instead of re-deriving them
     t.lut_g = sp.lut;
     return t;
 }

@@ -9,7 +9,14 @@
 #pragma once
 #include "mapf_device.cuh"
 
+#ifndef MAPF_MAX_THREADS
 #define MAPF_MAX_THREADS 512  // largest CTA the hot kernels are launched with
+#endif
+// Register budget of the step kernel: up to 6 agents everything fits 64 registers (2 CTAs of 512 or 4 of 256
+// threads per SM, measured best on the 4-agent workload); more agents get the full 128.
+#ifndef MAPF_MIN_BLOCKS
+#define MAPF_MIN_BLOCKS(N) ((N) <= 6 ? 2 : 1)
+#endif
 
 // =====================================================================================================
 // Move-table construction from the obstacle bitmap (ctx creation; not a hot kernel)
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(256) k_count(DevSpec sp, const u64 *__restrict
         decode_state<N, WORDS>(sp, lo, hi, cell);
         decode_action<N>(a, act);
         i64 len = 1;
-        if (!is_terminal<N>(sp, cell)) {
+        if (!is_terminal<N>(sp, cell, lo, hi)) {
 #pragma unroll
             for (int i = 0; i < N; ++i) len *= (i64)ENT_K(__ldg(sp.lut + cell[i] * 5 + act[i]));
         }
@@ -307,7 +314,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
         }
         if (!ready) { tables_wait<LUTS>(smem); ready = true; }
         if (b < B) {
-            const bool term = is_terminal<N>(sp, cell);
+            const bool term = is_terminal<N>(sp, cell, lo, hi);
             len = 1;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -447,7 +454,7 @@ template <int N, int WORDS, bool LUTS, bool TAPE>
 __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &tb, const EnvIn<N> &in,
                                            const double *__restrict__ u, u32 opts, int (&nxt)[N]) {
     double total;
-    const bool term = is_terminal<N>(sp, in.cell);
+    const bool term = is_terminal<N>(sp, in.cell, in.lo, in.hi);
     const u32 act_base = LUTS ? tb.lut : 0u;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -462,23 +469,21 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
         } else {
             const uint2 t = lds_u32x2<MAPF_SMEM_THR>(row);
             const u32 w = in.w[i];
-            pick = (w > t.x ? 1u : 0u) + (w > t.y ? 1u : 0u);
+            pick = count_below(w, t.x, t.y);
         }
         nxt[i] = (int)ent_dest(e, pick);
         const double pi = lds_f64<MAPF_SMEM_PP>(row + pick * 8u);
         total = i == 0 ? pi : __dmul_rn(total, pi);  // 1 * p0 * p1 * ... (mapf_env.py:250,257)
     }
     const bool clash = has_clash<N>(in.cell, nxt);
-    bool goal = true;
-#pragma unroll
-    for (int i = 0; i < N; ++i) goal = goal && (nxt[i] == (int)sp.goal[i]);
-    const int kind = clash ? 1 : (goal ? 2 : 0);
     EnvOut out;
+    encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
+    const bool goal = out.lo == sp.sgoal[0] && out.hi == sp.sgoal[1];  // every agent on its goal
+    const int kind = clash ? 1 : (goal ? 2 : 0);
     out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + parked_agents<N>(sp, in.cell, in.act)) * 8u);
     out.prob = total;
     out.done = kind != 0 ? 1u : 0u;
     out.coll = clash ? 1u : 0u;
-    encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
     if (term) {  // (s, 0, True, {"prob": 0})  (mapf_env.py:238-240): a no-op that consumes no draw
         out.lo = in.lo; out.hi = in.hi; out.reward = 0.0; out.prob = 0.0; out.done = 1u; out.coll = 0u;
 #pragma unroll
@@ -500,31 +505,57 @@ __device__ __forceinline__ u32 random_action(const DevSpec &sp, const PhiloxKeys
 // EPT = envs per thread per iteration.  EPT == 2 uses 128-bit loads/stores for the 8-byte fields (and 16-bit
 // stores for the two flag bytes); the launcher picks it only when B is even and every pointer is 16-byte aligned.
 // B < 2**31 (the launcher splits larger batches), so every index is 32-bit and an address is one wide multiply-add.
+// The inputs of the thread's next iteration are loaded before the current one is computed (software prefetch).
+template <int WORDS, int EPT>
+struct RawIn {
+    u64 lo[EPT], hi[EPT];
+    u32 a[EPT];
+};
+
+template <int WORDS, int EPT>
+__device__ __forceinline__ void load_raw(const u64 *states, const int *__restrict__ actions, u32 it, RawIn<WORDS, EPT> &r) {
+    if (EPT == 2 && WORDS == 1) {
+        const ulonglong2 s2 = reinterpret_cast<const ulonglong2 *>(states)[it];
+        const int2 a2 = reinterpret_cast<const int2 *>(actions)[it];
+        r.lo[0] = s2.x; r.lo[EPT - 1] = s2.y; r.hi[0] = 0; r.hi[EPT - 1] = 0;
+        r.a[0] = (u32)a2.x; r.a[EPT - 1] = (u32)a2.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            load_state<WORDS>(states, it * EPT + q, r.lo[q], r.hi[q]);
+            r.a[q] = (u32)actions[it * EPT + q];
+        }
+    }
+}
+
 template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
-__global__ void __launch_bounds__(MAPF_MAX_THREADS)
+__global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
 k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
        const double *__restrict__ uniforms, u64 step, u64 env0, u32 opts, u64 *next_states,
        double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue (table staging) while
+    // this grid drains, and do our own prologue before waiting for the previous grid's results to be visible.
+    asm volatile("griddepcontrol.launch_dependents;");
     SmemTables tb = tables_begin<LUTS>(sp, smem);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     bool ready = false;
     const u32 n_items = B / EPT;
-    for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+    const u32 stride = gridDim.x * blockDim.x;
+    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    RawIn<WORDS, EPT> raw;
+    if (it < n_items) load_raw<WORDS, EPT>(states, actions, it, raw);
+    while (it < n_items) {
         EnvIn<N> in[EPT];
         const u32 b = it * EPT;
-        if (EPT == 2 && WORDS == 1) {
-            const ulonglong2 s2 = reinterpret_cast<const ulonglong2 *>(states)[it];
-            const int2 a2 = reinterpret_cast<const int2 *>(actions)[it];
-            in[0].lo = s2.x; in[0].hi = 0; in[EPT - 1].lo = s2.y; in[EPT - 1].hi = 0;
-            decode_action<N>((u32)a2.x, in[0].act);
-            decode_action<N>((u32)a2.y, in[EPT - 1].act);
-        } else {
 #pragma unroll
-            for (int q = 0; q < EPT; ++q) {
-                load_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
-                decode_action<N>((u32)actions[b + q], in[q].act);
-            }
+        for (int q = 0; q < EPT; ++q) {
+            in[q].lo = raw.lo[q];
+            in[q].hi = raw.hi[q];
+            decode_action<N>(raw.a[q], in[q].act);
         }
+        const u32 it_next = it + stride;
+        if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             decode_state<N, WORDS>(sp, in[q].lo, in[q].hi, in[q].cell);
@@ -555,6 +586,7 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
             done[b] = (u8)o[0].done;
             coll[b] = (u8)o[0].coll;
         }
+        it = it_next;
     }
     if (!ready) tables_wait<LUTS>(smem);
 }

@@ -15,8 +15,8 @@ def main():
     mode = os.environ.get("TIME_MODE", "step")
     env = bench.make_env(device=0)
     eng = env.engine
-    B, dev = bench.ENVS_PER_GPU, torch.device("cuda", 0)
-    R = 16
+    B, dev = int(os.environ.get("TIME_B", bench.ENVS_PER_GPU)), torch.device("cuda", 0)
+    R = max(2, min(16, (1 << 24) // B))
     g = torch.Generator(device=dev)
     g.manual_seed(1)
     states = [eng.states_from_ints([eng.s0]).expand(B).contiguous()]
@@ -32,19 +32,38 @@ def main():
             states.append(out[0].clone())
     torch.cuda.synchronize()
     best = 1e9
-    K = 100
-    for rep in range(6):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    K = 96
+    use_graph = os.environ.get("TIME_GRAPH", "0") == "1"
+
+    def run_k():
         for i in range(K):
             j = i % R
             eng.step(states[j], actions[j], seed=3, step_index=100 + i, auto_reset=True, out=outs[j])
+
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run_k()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run_k()
+        torch.cuda.synchronize()
+    for rep in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            run_k()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / K * 1e3)
     cs = eng.checksum(outs[0][0], outs[0][2], outs[0][1], outs[0][3].to(torch.uint8) + 2 * outs[0][4].to(torch.uint8))
-    print("%-28s thr=%s bps=%s ept=%s  %7.2f us/step  %5.1f%% roofline  cs=%d" % (
-        tag, os.environ.get("MAPF_THREADS", "-"), os.environ.get("MAPF_BLOCKS_PER_SM", "-"),
+    print("%-8s graph=%s B=%d thr=%s bps=%s ept=%s  %7.2f us/step  %5.1f%% roofline  cs=%d" % (
+        tag, os.environ.get("TIME_GRAPH", "0"), B, os.environ.get("MAPF_THREADS", "-"), os.environ.get("MAPF_BLOCKS_PER_SM", "-"),
         os.environ.get("MAPF_STEP_EPT", "-"), best, 100 * B * 38 / (best * 1e-6) / 1e9 / 6436.1,
         int(cs.cpu()[7].item()) & 0xffffffff), flush=True)
 
