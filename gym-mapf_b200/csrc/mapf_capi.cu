@@ -304,13 +304,13 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
             double x = ceil(acc * 4294967296.0);
             if (x > 4294967296.0) x = 4294967296.0;
             if (x < 1.0) x = 1.0;  // cannot happen: the first merged outcome has positive probability
-            sp.thr[p][j] = (u32)((u64)x - 1);
+            sp.thr[p][j] = ~(u32)((u64)x - 1);  // stored complemented, see count_below()
         }
         // the device-side sampling mode counts thresholds below the draw, which needs the pattern's last
         // cumulative probability to reach 1 (within 2**-32): true whenever right_fail + left_fail <= 1
         const int k = (ctx->pat_triple[p] & 7u ? 1 : 0) + ((ctx->pat_triple[p] >> 3) & 7u ? 1 : 0) +
                       ((ctx->pat_triple[p] >> 6) & 7u ? 1 : 0);
-        if (sp.thr[p][k - 1] != 0xffffffffu) ctx->philox_ok = false;
+        if (sp.thr[p][k - 1] != 0u) ctx->philox_ok = false;  // ~(2**32 - 1)
     }
     // ---- rewards (mapf_env.py:225-235, 436-446), one entry per number of parked agents
     for (int k = 0; k <= n; ++k) {

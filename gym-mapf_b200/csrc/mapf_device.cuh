@@ -67,7 +67,7 @@ struct DevSpec {
     u16 goal[16];      // goal cell per agent (mapf_env.py:158)
     u16 start[16];
     // per merge pattern, for merged outcome j = 0..2 (slot 3 pads to 16 / 32 bytes):
-    u32 thr[MAPF_MAX_PATTERNS][8];     // largest 32-bit draw w with cumsum_j > w * 2**-32 (32-byte rows)
+    u32 thr[MAPF_MAX_PATTERNS][8];     // ~T_j, T_j = largest 32-bit draw w with cumsum_j > w * 2**-32 (32-byte rows)
     double cum[MAPF_MAX_PATTERNS][4];  // np.cumsum of the merged probabilities (mapf_env.py:255)
     double pp[MAPF_MAX_PATTERNS][4];   // merged probabilities
     double reward[3 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living][parked agents]
@@ -217,11 +217,12 @@ __device__ __forceinline__ int parked_agents(const DevSpec &sp, const int (&prev
     return k;
 }
 
-// (w > a) + (w > b) with the carry flag: two borrow-generating subtractions
-__device__ __forceinline__ u32 count_below(u32 w, u32 a, u32 b) {
+// (w > a) + (w > b) from the carry flag: w > a  <=>  w + ~a carries out of 32 bits.  The thresholds are stored
+// complemented (na = ~a, nb = ~b) so each comparison is one carry-generating add.
+__device__ __forceinline__ u32 count_below(u32 w, u32 na, u32 nb) {
     u32 t, n;
-    asm("{\n\t.reg .u32 t0;\n\tsub.cc.u32 t0, %2, %1;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(t) : "r"(w), "r"(a));
-    asm("{\n\t.reg .u32 t0;\n\tsub.cc.u32 t0, %2, %1;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(n) : "r"(w), "r"(b), "r"(t));
+    asm("{\n\t.reg .u32 t0;\n\tadd.cc.u32 t0, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(t) : "r"(w), "r"(na));
+    asm("{\n\t.reg .u32 t0;\n\tadd.cc.u32 t0, %1, %2;\n\taddc.u32 %0, %3, 0;\n\t}" : "=r"(n) : "r"(w), "r"(nb), "r"(t));
     return n;
 }
 

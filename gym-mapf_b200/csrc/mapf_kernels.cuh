@@ -447,7 +447,7 @@ __device__ __forceinline__ void env_draws(const PhiloxKeys &K, u64 env, u64 step
 
 // One sampled joint transition.  TAPE: agent i's uniform is u[i] (a replayed reference draw) and the choice is
 // `(cumsum > u).argmax()` in fp64 (mapf_env.py:255).  Otherwise the draw is the 32-bit Philox word w, u = w * 2**-32,
-// and the same comparison is made on integers: cumsum_j > u  <=>  w <= thr_j.  The host guarantees that the last
+// and the same comparison is made on integers: cumsum_j > u  <=>  w <= T_j (the table holds ~T_j).  The host guarantees that the last
 // threshold of every pattern is 2**32 - 1 (the probabilities of a pattern add up to 1), so the index is simply the
 // number of thresholds below w.
 template <int N, int WORDS, bool LUTS, bool TAPE>
