@@ -208,7 +208,10 @@ def run_ours(args):
     env = make_env(device=local)
     eng = env.engine
     B, K, W = ENVS_PER_GPU, args.steps, args.warmup
-    env_offset = rank * B
+    from gym_mapf_b200 import sharding
+    shard = sharding.env_shard(world * B, world, rank)   # contiguous slice of the global env batch, no exchange step
+    assert shard.count == B
+    env_offset = shard.begin
     seed = 20261018
 
     # ---- ring of pre-filled slots: slot j holds the states after j random steps from reset (auto-reset on)
@@ -296,12 +299,7 @@ def run_ours(args):
     ns, reward, prob, done, coll = outs[j]
     flags = done.to(torch.uint8) + 2 * coll.to(torch.uint8)
     cs = eng.checksum(ns, prob, reward, flags, index_base=env_offset)
-    if world > 1:
-        gathered = [torch.zeros_like(cs) for _ in range(world)]
-        dist.all_gather(gathered, cs)
-    else:
-        gathered = [cs]
-    shard_sums = [[int(x) for x in c.cpu().numpy().view(np.uint64)] for c in gathered]
+    shard_sums = [[int(x) for x in words] for words in sharding.gather_words(cs)]
 
     # ---- end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> step -> D2H, every step
     e2e = None
