@@ -559,8 +559,10 @@ static int expand_impl(const mapf_ctx *ctx, bool range, const void *states, cons
     DeviceGuard g(ctx->device);
     DevSpec sp = ctx->sp;
     void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_ptr, &next_state, &prob, &reward, &flags};
-    const int64_t warps_needed = (B + 31) / 32;
-    const int grid = grid_for(warps_needed * 32, ctx->threads, range ? ctx->grid_expand_range : ctx->grid_expand);
+    // Work is cut by records (at least 32 per warp); their number is only known on the device, B * 3**n bounds it.
+    const double rec_max = (double)B * (double)ctx->info.max_row_len;
+    const int64_t lanes = rec_max > 4e18 ? (int64_t)4e18 : (int64_t)rec_max;
+    const int grid = grid_for(lanes, ctx->threads, range ? ctx->grid_expand_range : ctx->grid_expand);
     LAUNCH(range ? ctx->ks.expand_range : ctx->ks.expand, grid, ctx->threads, ctx->smem_expand, stream, args);
     return MAPF_OK;
 }
@@ -658,8 +660,7 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         if (use_pdl) {
             // programmatic stream serialization: this launch may begin (up to its griddepcontrol.wait) while the
             // previous kernel of the stream is still draining
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof(cfg));
+            cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
             cfg.blockDim = dim3(ctx->threads);
             cfg.dynamicSmemBytes = ctx->smem_base;

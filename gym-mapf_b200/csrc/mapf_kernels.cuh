@@ -271,22 +271,45 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
 // =====================================================================================================
 // Expand: P[s][a] rows as CSR records (mapf_env.py:448-479)
 // =====================================================================================================
-// A warp takes 32 consecutive rows at a time.
-//   phase A (lane = row):     decode (s, a), terminal test, fetch the N move-table entries, row length;
-//                             the row descriptor goes to the warp's shared-memory slab
-//   phase B (lane = record):  the rows' records are consecutive in the output (row_ptr is their exclusive scan),
-//                             so record j of the 32-row batch goes to base + j: every store of the warp is one
-//                             contiguous, fully coalesced segment
+// Work is partitioned by OUTPUT RECORDS, not by rows: the M = row_ptr[B] records are cut into one contiguous,
+// 32-aligned range per warp, so a row of 3**13 records and a row of one record cost what they write.  A warp
+//   0. finds the row holding its first record with a 32-ary search of row_ptr (one probe per lane and step),
+//   A. (lane = row) decodes 32 consecutive rows: (s, a) -> cells, terminal test, the N move-table entries, row length,
+//      and whether ANY pair of agents can conflict in this row at all (their destination sets touch); the row
+//      descriptors go to the warp's shared-memory slab,
+//   B. (lane = record) walks its record range in windows of 32 consecutive records: record w + lane belongs to lane
+//      `lane`, so every store of the warp is one contiguous, fully coalesced segment.  The row of a record comes
+//      from a warp-wide OR of "my row starts at position p of this window" bits (REDUX) and a popcount.
 template <int N>
 struct ExpandSlab {
     u64 ent[N][32];   // move-table entry of agent i for row r
     u64 st[2][32];    // the row's own state (terminal rows re-emit it)
-    u32 pref[33];     // exclusive scan of the 32 row lengths
-    u32 pad;
+    u32 pref[32];     // first record of row r, relative to the batch's first record
     u16 prev[N][32];  // current cell of agent i
     u8 parked[32];    // SoC: agents parked on their goal choosing STAY
-    u8 term[32];
+    u8 flag[32];      // bit 0: terminal state; bit 1: some pair of agents can conflict
 };
+
+// Can agents i and j conflict in any outcome of this row?  A vertex conflict needs a common destination, a swap
+// needs each one's current cell among the other's destinations: both imply that the sets {current cell} + {merged
+// destinations} intersect (unused destination slots repeat slot 0).  Exact in the "no" direction, which is all the
+// pre-filter needs.
+template <int N>
+__device__ __forceinline__ bool any_pair_can_conflict(const int (&cell)[N], const u64 (&ent)[N]) {
+    bool live = false;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const u32 a0 = (u32)cell[i], a1 = (u32)ent[i] & 0xffffu, a2 = ((u32)ent[i]) >> 16, a3 = (u32)(ent[i] >> 32) & 0xffffu;
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            const u32 b0 = (u32)cell[j], b1 = (u32)ent[j] & 0xffffu, b2 = ((u32)ent[j]) >> 16,
+                      b3 = (u32)(ent[j] >> 32) & 0xffffu;
+            live = live || a0 == b1 || a0 == b2 || a0 == b3 || a1 == b0 || a1 == b1 || a1 == b2 || a1 == b3 ||
+                   a2 == b0 || a2 == b1 || a2 == b2 || a2 == b3 || a3 == b0 || a3 == b1 || a3 == b2 || a3 == b3;
+        }
+    }
+    return live;
+}
 
 template <int N, int WORDS, bool LUTS, bool RANGE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
@@ -295,99 +318,137 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
          double *__restrict__ reward, u8 *__restrict__ flags) {
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables tb = tables_begin<LUTS>(sp, smem);
+    const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 lane_le = 0xffffffffu >> (31 - lane);
     ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
-    const i64 n_batches = (B + 31) >> 5;
-    const i64 warps_total = (i64)gridDim.x * (blockDim.x >> 5);
-    bool ready = false;
-    for (i64 batch = (i64)blockIdx.x * (blockDim.x >> 5) + wid; batch < n_batches; batch += warps_total) {
-        // ---------------- phase A
-        const i64 b = batch * 32 + lane;
-        u32 len = 0;
-        int cell[N], act[N];
-        u64 lo = 0, hi = 0;
-        if (b < B) {
-            u32 a;
-            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
-            decode_state<N, WORDS>(sp, lo, hi, cell);
-            decode_action<N>(a, act);
+    const i64 M = row_ptr[B];
+    const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
+    const i64 chunk = ((M + 32 * n_warps - 1) / (32 * n_warps)) * 32;  // records per warp, a multiple of 32
+    const i64 lo = ((i64)blockIdx.x * (blockDim.x >> 5) + wid) * chunk;
+    const i64 hi = lo + chunk < M ? lo + chunk : M;
+    tables_wait<LUTS>(smem);
+    if (lo >= hi) return;
+    // ---------------- 0: the row r with row_ptr[r] <= lo < row_ptr[r + 1]
+    i64 r;
+    {
+        i64 a = 0, b = B;  // row_ptr[a] <= lo < row_ptr[b]
+        while (b - a > 1) {
+            const i64 step = (b - a + 31) >> 5;
+            i64 p = a + (i64)(lane + 1) * step;
+            p = p < b ? p : b;
+            const int c = __popc(__ballot_sync(FULL, row_ptr[p] <= lo));  // probes are increasing: a prefix is true
+            const i64 nb = a + (i64)(c + 1) * step;
+            a += (i64)c * step;
+            b = nb < b ? nb : b;
         }
-        if (!ready) { tables_wait<LUTS>(smem); ready = true; }
-        if (b < B) {
-            const bool term = is_terminal<N>(sp, cell, lo, hi);
+        r = a;
+    }
+    for (;;) {
+        // ---------------- phase A: rows r .. r + 31 (those that start before `hi`)
+        const i64 b = r + lane;
+        const i64 start = b < B ? row_ptr[b] : M;
+        const i64 batch_begin = __shfl_sync(FULL, start, 0);
+        const bool need = b < B && start < hi;
+        u32 len = 0;
+        if (need) {
+            u64 slo, shi;
+            u32 a;
+            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, slo, shi, a);
+            int cell[N], act[N];
+            u64 ent[N];
+            decode_state<N, WORDS>(sp, slo, shi, cell);
+            decode_action<N>(a, act);
+            const bool term = is_terminal<N>(sp, cell, slo, shi);
             len = 1;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                u64 e = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
-                sl.ent[i][lane] = e;
+                ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
+                sl.ent[i][lane] = ent[i];
                 sl.prev[i][lane] = (u16)cell[i];
-                len *= ENT_K(e);
+                len *= ENT_K(ent[i]);
             }
             if (term) len = 1;
-            sl.st[0][lane] = lo;
-            sl.st[1][lane] = hi;
+            sl.st[0][lane] = slo;
+            sl.st[1][lane] = shi;
             sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
-            sl.term[lane] = term ? 1 : 0;
+            sl.flag[lane] = (u8)((term ? 1 : 0) | (any_pair_can_conflict<N>(cell, ent) ? 2 : 0));
         }
         u32 incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+            const u32 y = __shfl_up_sync(FULL, incl, o);
             if (lane >= o) incl += y;
         }
-        sl.pref[lane + 1] = incl;
-        if (lane == 0) sl.pref[0] = 0;
-        const i64 out0 = row_ptr[batch * 32];
+        const u32 total = __shfl_sync(FULL, incl, 31);
+        const int myrel = (int)(incl - len);  // first record of my row, relative to batch_begin
+        sl.pref[lane] = (u32)myrel;
         __syncwarp();
-        // ---------------- phase B
-        const u32 total = sl.pref[32];
-        int r = 0;
-        for (u32 j = lane; j < total; j += 32) {
-            while (j >= sl.pref[r + 1]) ++r;
-            u32 o = j - sl.pref[r];
-            const i64 idx = out0 + j;
-            if (sl.term[r]) {  // [((1.0, False), s, 0, True)]  (mapf_env.py:455-456)
-                store_state<WORDS>(next_state, idx, sl.st[0][r], sl.st[1][r]);
+        // ---------------- phase B: records [first, last) of this batch, in 32-aligned windows
+        const i64 batch_end = batch_begin + total;
+        const i64 first = lo > batch_begin ? lo : batch_begin;
+        const i64 last = hi < batch_end ? hi : batch_end;
+        const int first_rel = (int)(first - batch_begin), last_rel = (int)(last - batch_begin);
+        i64 w = first & ~31ll;
+        int wrel = (int)(w - batch_begin);  // may be negative in a batch's first window
+        int rows_before = __popc(__ballot_sync(FULL, need && myrel < wrel));  // rows starting before the window
+        for (; wrel < last_rel; wrel += 32, w += 32) {
+            const bool inwin = need && myrel >= wrel && myrel < wrel + 32;
+            const u32 heads = __reduce_or_sync(FULL, inwin ? 1u << (myrel - wrel) : 0u);
+            const int row = rows_before + __popc(heads & lane_le) - 1;
+            rows_before += __popc(heads);
+            const int rel = wrel + lane;
+            if (rel < first_rel || rel >= last_rel) continue;
+            const i64 idx = w + lane;
+            const u32 flag = sl.flag[row];
+            if (flag & 1u) {  // [((1.0, False), s, 0, True)]  (mapf_env.py:455-456)
+                store_state<WORDS>(next_state, idx, sl.st[0][row], sl.st[1][row]);
                 prob[idx] = 1.0;
                 reward[idx] = 0.0;
                 flags[idx] = 1;
                 continue;
             }
+            u32 o = (u32)rel - sl.pref[row];
             // outcome digits: itertools.product, the LAST agent's digit moves fastest (mapf_env.py:467)
-            int nxt[N], prv[N];
+            int nxt[N];
             u32 pj[N];
 #pragma unroll
             for (int i = N - 1; i >= 0; --i) {
-                const u64 e = sl.ent[i][r];
+                const u64 e = sl.ent[i][row];
                 const u32 k = ENT_K(e);
-                u32 d;
-                if (k == 1) { d = 0; }
-                else if (k == 2) { d = o & 1u; o >>= 1; }
-                else { u32 q = __umulhi(o, 0xAAAAAAABu) >> 1; d = o - 3u * q; o = q; }
+                // o = q * k + d with k in {1, 2, 3}: q = floor(2o * m / 2**32), m = ceil(2**31 / k)
+                const u32 m = k == 3u ? 0x2AAAAAABu : (0x80000000u >> (k - 1u));
+                const u32 q = __umulhi(o + o, m);
+                const u32 d = o - q * k;
+                o = q;
                 nxt[i] = (int)ent_dest(e, d);
                 pj[i] = ENT_POFF(e) + d * 8u;
-                prv[i] = (int)sl.prev[i][r];
             }
             // probability: left-to-right product (mapf_env.py:468)
             double p = lds_f64<MAPF_SMEM_PP>(tb.base + pj[0]);
 #pragma unroll
             for (int i = 1; i < N; ++i) p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + pj[i]));
             // reward / done / collision (mapf_env.py:225-235): clash beats goal
-            const bool clash = has_clash<N>(prv, nxt);
-            bool goal = true;
+            bool clash = false;
+            if (flag & 2u) {
+                int prv[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) goal = goal && (nxt[i] == (int)sp.goal[i]);
-            const int kind = clash ? 1 : (goal ? 2 : 0);
+                for (int i = 0; i < N; ++i) prv[i] = (int)sl.prev[i][row];
+                clash = has_clash<N>(prv, nxt);
+            }
             u64 nlo, nhi;
             encode_state<N, WORDS>(sp, nxt, nlo, nhi);
+            const bool goal = nlo == sp.sgoal[0] && nhi == sp.sgoal[1];  // every agent on its goal
+            const int kind = clash ? 1 : (goal ? 2 : 0);
             store_state<WORDS>(next_state, idx, nlo, nhi);
             prob[idx] = p;
-            reward[idx] = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[r]) * 8u);
+            reward[idx] = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[row]) * 8u);
             flags[idx] = (u8)((kind != 0 ? 1 : 0) | (clash ? 2 : 0));
         }
+        if (batch_end >= hi || r + 32 >= B) break;
+        r += 32;
         __syncwarp();
     }
-    if (!ready) tables_wait<LUTS>(smem);  // never leave a CTA while its bulk copy is in flight
 }
 
 // =====================================================================================================
