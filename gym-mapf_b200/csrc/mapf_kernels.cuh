@@ -280,20 +280,50 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
 //   B. (lane = record) walks its record range in windows of 32 consecutive records: record w + lane belongs to lane
 //      `lane`, so every store of the warp is one contiguous, fully coalesced segment.  The row of a record comes
 //      from a warp-wide OR of "my row starts at position p of this window" bits (REDUX) and a popcount.
+// floor(2**63 / 3**b), b = 0..13
+static __constant__ u64 RECIP_POW3[14] = {
+    9223372036854775808ull, 3074457345618258602ull, 1024819115206086200ull, 341606371735362066ull,
+    113868790578454022ull,  37956263526151340ull,   12652087842050446ull,   4217362614016815ull,
+    1405787538005605ull,    468595846001868ull,     156198615333956ull,     52066205111318ull,
+    17355401703772ull,      5785133901257ull};
+
+#define EXPAND_MAX_PAIRS 4
+#ifndef EXPAND_LIST_MIN_AGENTS
+#define EXPAND_LIST_MIN_AGENTS 8
+#endif
 template <int N>
 struct ExpandSlab {
     u64 ent[N][32];   // move-table entry of agent i for row r
     u64 st[2][32];    // the row's own state (terminal rows re-emit it)
+    u64 rcp[32];      // floor(2**63 / row length): turns a record's index within the row into a 32-bit fraction
     u32 pref[32];     // first record of row r, relative to the batch's first record
     u16 prev[N][32];  // current cell of agent i
+    u32 pair[EXPAND_MAX_PAIRS][32];  // descriptors of the pairs of agents that can conflict in row r
     u8 parked[32];    // SoC: agents parked on their goal choosing STAY
-    u8 flag[32];      // bit 0: terminal state; bit 1: some pair of agents can conflict
+    u8 flag[32];      // bit 0: terminal state; bits 1..3: number of pair descriptors; bit 4: too many, test all pairs
 };
 
-// Can agents i and j conflict in any outcome of this row?  A vertex conflict needs a common destination, a swap
-// needs each one's current cell among the other's destinations: both imply that the sets {current cell} + {merged
-// destinations} intersect (unused destination slots repeat slot 0).  Exact in the "no" direction, which is all the
-// pre-filter needs.
+// Which pairs of agents can conflict in some outcome of a row?  A vertex conflict needs a common destination, a
+// swap needs each agent's current cell among the other's destinations: both imply that the sets {current cell} +
+// {merged destinations} of the two agents intersect (unused destination slots repeat slot 0).  That test rejects
+// almost every pair; a pair that passes gets a descriptor
+//     bits 0..4: 2i     bits 5..9: 2j     bits 10..18: conflict mask, bit 3a+b set when outcome a of agent i and
+//                                                      outcome b of agent j conflict (mapf_env.py:378-389)
+// so that phase B tests a record with two digit extractions and one bit test per listed pair instead of all
+// N(N-1)/2 pairs.  Pairs beyond EXPAND_MAX_PAIRS switch the row to the all-pairs test.
+static __device__ __noinline__ u32 pair_conflict_mask(u32 prev_i, u64 ei, u32 prev_j, u64 ej) {
+    u32 mask = 0;
+    for (u32 a = 0; a < 3; ++a) {
+        const u32 da = (u32)(ei >> (16 * a)) & 0xffffu;
+        for (u32 b = 0; b < 3; ++b) {
+            const u32 db = (u32)(ej >> (16 * b)) & 0xffffu;
+            const bool vertex = da == db, swap = da == prev_j && db == prev_i;
+            mask |= (vertex || swap) ? 1u << (3 * a + b) : 0u;
+        }
+    }
+    return mask;
+}
+
 template <int N>
 __device__ __forceinline__ bool any_pair_can_conflict(const int (&cell)[N], const u64 (&ent)[N]) {
     bool live = false;
@@ -309,6 +339,30 @@ __device__ __forceinline__ bool any_pair_can_conflict(const int (&cell)[N], cons
         }
     }
     return live;
+}
+
+template <int N>
+__device__ __forceinline__ u32 list_conflict_pairs(const int (&cell)[N], const u64 (&ent)[N], u32 (*pair)[32], int lane) {
+    u32 count = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const u32 a0 = (u32)cell[i], a1 = (u32)ent[i] & 0xffffu, a2 = ((u32)ent[i]) >> 16, a3 = (u32)(ent[i] >> 32) & 0xffffu;
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            const u32 b0 = (u32)cell[j], b1 = (u32)ent[j] & 0xffffu, b2 = ((u32)ent[j]) >> 16,
+                      b3 = (u32)(ent[j] >> 32) & 0xffffu;
+            const bool touch = a0 == b1 || a0 == b2 || a0 == b3 || a1 == b0 || a1 == b1 || a1 == b2 || a1 == b3 ||
+                               a2 == b0 || a2 == b1 || a2 == b2 || a2 == b3 || a3 == b0 || a3 == b1 || a3 == b2 || a3 == b3;
+            if (touch) {
+                const u32 mask = pair_conflict_mask(a0, ent[i], b0, ent[j]);
+                if (mask) {
+                    if (count < EXPAND_MAX_PAIRS) pair[count][lane] = (u32)(2 * i) | ((u32)(2 * j) << 5) | (mask << 10);
+                    ++count;
+                }
+            }
+        }
+    }
+    return count;
 }
 
 template <int N, int WORDS, bool LUTS, bool RANGE>
@@ -361,18 +415,28 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             decode_action<N>(a, act);
             const bool term = is_terminal<N>(sp, cell, slo, shi);
             len = 1;
+            u32 twos = 0, threes = 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
                 sl.ent[i][lane] = ent[i];
                 sl.prev[i][lane] = (u16)cell[i];
-                len *= ENT_K(ent[i]);
+                const u32 k = ENT_K(ent[i]);
+                len *= k;
+                twos += k == 2u ? 1u : 0u;
+                threes += k == 3u ? 1u : 0u;
             }
             if (term) len = 1;
+            sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
             sl.st[0][lane] = slo;
             sl.st[1][lane] = shi;
             sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
-            sl.flag[lane] = (u8)((term ? 1 : 0) | (any_pair_can_conflict<N>(cell, ent) ? 2 : 0));
+            // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
+            // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
+            u32 n_pairs;
+            if (N >= EXPAND_LIST_MIN_AGENTS) n_pairs = term ? 0u : list_conflict_pairs<N>(cell, ent, sl.pair, lane);
+            else n_pairs = any_pair_can_conflict<N>(cell, ent) ? EXPAND_MAX_PAIRS + 1u : 0u;
+            sl.flag[lane] = (u8)((term ? 1u : 0u) | (n_pairs <= EXPAND_MAX_PAIRS ? n_pairs << 1 : 16u));
         }
         u32 incl = len;
 #pragma unroll
@@ -408,21 +472,24 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
                 flags[idx] = 1;
                 continue;
             }
-            u32 o = (u32)rel - sl.pref[row];
-            // outcome digits: itertools.product, the LAST agent's digit moves fastest (mapf_env.py:467)
+            // Outcome digits: itertools.product, agent 0 slowest (mapf_env.py:467).  With T = row length and o the
+            // record's index in the row, x = (o + 1/2) / T as a 32-bit fraction; multiplying by k_0 leaves digit 0 in
+            // the integer part and the fraction of the remaining digits, and so on: ONE wide multiply per agent.
+            // (T <= 3**13 < 2**21: the 2**-32 truncation of x grows to at most 2**-11 of a digit, the half-unit
+            // offset keeps every digit 2**-22 away from an integer boundary.)
+            const u32 o = (u32)rel - sl.pref[row];
+            u32 x = (u32)(((u64)(2u * o + 1u) * sl.rcp[row]) >> 32);
             int nxt[N];
-            u32 pj[N];
+            u32 pj[N], dv = 0;  // dv: the digits, two bits per agent
 #pragma unroll
-            for (int i = N - 1; i >= 0; --i) {
+            for (int i = 0; i < N; ++i) {
                 const u64 e = sl.ent[i][row];
-                const u32 k = ENT_K(e);
-                // o = q * k + d with k in {1, 2, 3}: q = floor(2o * m / 2**32), m = ceil(2**31 / k)
-                const u32 m = k == 3u ? 0x2AAAAAABu : (0x80000000u >> (k - 1u));
-                const u32 q = __umulhi(o + o, m);
-                const u32 d = o - q * k;
-                o = q;
+                const u64 wide = (u64)x * (u64)((u32)(e >> 56));  // bits 58..63 of an entry are zero: this is k
+                const u32 d = (u32)(wide >> 32);
+                x = (u32)wide;
                 nxt[i] = (int)ent_dest(e, d);
                 pj[i] = ENT_POFF(e) + d * 8u;
+                if (N >= EXPAND_LIST_MIN_AGENTS) dv += d << (2 * i);
             }
             // probability: left-to-right product (mapf_env.py:468)
             double p = lds_f64<MAPF_SMEM_PP>(tb.base + pj[0]);
@@ -430,11 +497,17 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             for (int i = 1; i < N; ++i) p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + pj[i]));
             // reward / done / collision (mapf_env.py:225-235): clash beats goal
             bool clash = false;
-            if (flag & 2u) {
+            if (flag & 16u) {
                 int prv[N];
 #pragma unroll
                 for (int i = 0; i < N; ++i) prv[i] = (int)sl.prev[i][row];
                 clash = has_clash<N>(prv, nxt);
+            } else if (N >= EXPAND_LIST_MIN_AGENTS) {
+                for (u32 q = 0; q < (flag >> 1); ++q) {
+                    const u32 desc = sl.pair[q][row];
+                    const u32 di = (dv >> (desc & 31u)) & 3u, dj = (dv >> ((desc >> 5) & 31u)) & 3u;
+                    clash = clash || ((desc >> (10u + 3u * di + dj)) & 1u);
+                }
             }
             u64 nlo, nhi;
             encode_state<N, WORDS>(sp, nxt, nlo, nhi);
