@@ -68,7 +68,9 @@ struct mapf_ctx {
     int n_patterns = 0;
     double probtab[8];                  // probability of a merged outcome, indexed by its candidate mask
     bool philox_ok = true;              // every pattern's probabilities add up to 1: device-side sampling is exact
-    u64 *d_lut = nullptr;
+    PatternTables pt;                   // host copy of the per-pattern tables (the device copy is in the image)
+    unsigned char *d_image = nullptr;   // DevSpec::image; the move table is its tail
+    u64 *d_lut = nullptr;               // = d_image + (MAPF_SMEM_LUT - MAPF_SMEM_IMG)
     u32 *d_cell_rc = nullptr, *d_colbits = nullptr, *d_colbase = nullptr;
     std::vector<u64> h_lut;
     std::vector<u32> h_cell_rc;
@@ -116,13 +118,26 @@ static FastDiv make_fastdiv(u64 d) {
 }
 
 static Div32 make_div32(u32 d) {
-    // round-DOWN magic: umulhi(x, magic) >> shift is floor(x / d) or one less, for every 32-bit x
+    // The dividend is a two-digit chunk x < d*d.  Round-up magic m = ceil(2**s / d): umulhi(x, m) >> (s - 32) is
+    // exact when (m*d - 2**s) * (d*d - 1) < 2**s; take the smallest s >= 32 with m < 2**32 that satisfies it.
     Div32 f;
+    f.pad = 0;
+    if (d <= 1) { f.magic = 0; f.shift = 0; f.fix = 0; return f; }  // x is always 0
+    const u128 xmax = (u128)d * d - 1;
+    for (int s = 32; s < 64; ++s) {
+        const u128 p = (u128)1 << s;
+        const u128 m = (p + d - 1) / d;
+        if (m >> 32) break;
+        const u128 e = m * d - p;
+        if (e * xmax < p) { f.magic = (u32)m; f.shift = (u32)(s - 32); f.fix = 0; return f; }
+    }
+    // round-DOWN magic: floor(x / d) or one less for every 32-bit x; the kernels fix it with one compare
     const int fl = 31 - __builtin_clz(d);
     f.shift = (u32)fl;
     const u64 p = 1ull << (32 + fl);
     const u64 m = p / d;
     f.magic = (u32)(m > 0xffffffffull ? 0xffffffffull : m);
+    f.fix = 1;
     return f;
 }
 
@@ -133,7 +148,7 @@ extern "C" void mapf_ctx_destroy(mapf_ctx *ctx) {
     if (!ctx) return;
     {
         DeviceGuard g(ctx->device);
-        cudaFree(ctx->d_lut);
+        cudaFree(ctx->d_image);
         cudaFree(ctx->d_cell_rc);
         cudaFree(ctx->d_colbits);
         cudaFree(ctx->d_colbase);
@@ -213,6 +228,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     ctx->device = device;
     DevSpec &sp = ctx->sp;
     memset(&sp, 0, sizeof(sp));
+    memset(&ctx->pt, 0, sizeof(ctx->pt));
     sp.n = n; sp.L = L; sp.H = H; sp.Wd = W;
     sp.soc = spec->criterion == MAPF_SOC ? 1 : 0;
 
@@ -297,27 +313,27 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         for (int j = 0; j < 3; ++j) {
             const u32 m = (ctx->pat_triple[p] >> (3 * j)) & 7u;
             const double pj = ctx->probtab[m];
-            sp.pp[p][j] = pj;
+            ctx->pt.pp[p][j] = pj;
             if (m) acc = j == 0 ? pj : acc + pj;  // np.cumsum: sequential fp64 adds (mapf_env.py:255)
-            sp.cum[p][j] = acc;
+            ctx->pt.cum[p][j] = acc;
             // largest 32-bit w with acc > w * 2**-32, i.e. w < acc * 2**32 (an exact scaling)
             double x = ceil(acc * 4294967296.0);
             if (x > 4294967296.0) x = 4294967296.0;
             if (x < 1.0) x = 1.0;  // cannot happen: the first merged outcome has positive probability
-            sp.thr[p][j] = ~(u32)((u64)x - 1);  // stored complemented, see count_below()
+            ctx->pt.thr[p][j] = ~(u32)((u64)x - 1);  // stored complemented, see count_below()
         }
         // the device-side sampling mode counts thresholds below the draw, which needs the pattern's last
         // cumulative probability to reach 1 (within 2**-32): true whenever right_fail + left_fail <= 1
         const int k = (ctx->pat_triple[p] & 7u ? 1 : 0) + ((ctx->pat_triple[p] >> 3) & 7u ? 1 : 0) +
                       ((ctx->pat_triple[p] >> 6) & 7u ? 1 : 0);
-        if (sp.thr[p][k - 1] != 0u) ctx->philox_ok = false;  // ~(2**32 - 1)
+        if (ctx->pt.thr[p][k - 1] != 0u) ctx->philox_ok = false;  // ~(2**32 - 1)
     }
     // ---- rewards (mapf_env.py:225-235, 436-446), one entry per number of parked agents
     for (int k = 0; k <= n; ++k) {
         const double live = sp.soc ? (double)(n - k) * spec->reward_of_living : spec->reward_of_living;
-        sp.reward[0 * MAPF_REW_STRIDE + k] = live;
-        sp.reward[1 * MAPF_REW_STRIDE + k] = spec->reward_of_clash + live;
-        sp.reward[2 * MAPF_REW_STRIDE + k] = spec->reward_of_goal + live;
+        ctx->pt.reward[0 * MAPF_REW_STRIDE + k] = live;
+        ctx->pt.reward[1 * MAPF_REW_STRIDE + k] = spec->reward_of_clash + live;
+        ctx->pt.reward[2 * MAPF_REW_STRIDE + k] = spec->reward_of_goal + live;
     }
 
     // ---- device side
@@ -344,8 +360,10 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
             return _rc;                                                                                \
         }                                                                                              \
     } while (0)
-    CTX_TRY(cudaMalloc(&ctx->d_lut, lut_pad));
-    CTX_TRY(cudaMemset(ctx->d_lut, 0, lut_pad));
+    const size_t image_head = MAPF_SMEM_LUT - MAPF_SMEM_IMG;  // pattern tables + action table
+    CTX_TRY(cudaMalloc(&ctx->d_image, image_head + lut_pad));
+    CTX_TRY(cudaMemset(ctx->d_image, 0, image_head + lut_pad));
+    ctx->d_lut = reinterpret_cast<u64 *>(ctx->d_image + image_head);
     CTX_TRY(cudaMalloc(&ctx->d_cell_rc, (size_t)L * sizeof(u32)));
     CTX_TRY(cudaMalloc(&ctx->d_colbits, colbits.size() * sizeof(u32)));
     CTX_TRY(cudaMalloc(&ctx->d_colbase, colbase.size() * sizeof(u32)));
@@ -364,8 +382,12 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         pats.count = ctx->n_patterns;
         for (int p = 0; p < ctx->n_patterns; ++p) pats.triple[p] = ctx->pat_triple[p];
         const int blocks = (H * W + 255) / 256 < sm_count * 4 ? (H * W + 255) / 256 : sm_count * 4;
-        k_build_moves<<<blocks, 256, bm_smem>>>(ctx->d_colbits, ctx->d_colbase, H, W, wpc, sp.cand_mask, pats, ctx->d_lut,
-                                                ctx->d_cell_rc);
+        GoalList goals;
+        memset(&goals, 0, sizeof(goals));
+        goals.n = n;
+        for (int i = 0; i < n && i < 16; ++i) goals.cell[i] = (u16)goal_id[i];
+        k_build_moves<<<blocks, 256, bm_smem>>>(ctx->d_colbits, ctx->d_colbase, H, W, wpc, sp.cand_mask, pats, goals,
+                                                ctx->d_lut, ctx->d_cell_rc);
         CTX_TRY(cudaGetLastError());
         CTX_TRY(cudaDeviceSynchronize());
     }
@@ -390,8 +412,35 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     const bool luts = MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.expand_slab_bytes <= smem_limit;
     if (!luts) ctx->threads = 256;
     sp.lut_smem = luts ? 1 : 0;
+    {
+        // shared-window address of the hot kernels' dynamic shared memory (they have no static shared memory)
+        u32 *d_probe = nullptr;
+        CTX_TRY(cudaMalloc(&d_probe, sizeof(u32)));
+        k_probe_smem<<<1, 32, 1024>>>(d_probe);
+        CTX_TRY(cudaGetLastError());
+        CTX_TRY(cudaMemcpy(&sp.smem_window, d_probe, sizeof(u32), cudaMemcpyDeviceToHost));
+        cudaFree(d_probe);
+        const u32 act0 = luts ? sp.smem_window + MAPF_SMEM_LUT : 0u;
+        if (act0 + 32u > 0xffffu) {
+            mapf_ctx_destroy(ctx);
+            return fail(MAPF_ERR_UNSUPPORTED, "shared-memory window 0x%x does not fit the 16-bit action table", sp.smem_window);
+        }
+        std::vector<unsigned char> head(image_head, 0);
+        memcpy(head.data() + (MAPF_SMEM_THR - MAPF_SMEM_IMG), ctx->pt.thr, sizeof(ctx->pt.thr));
+        memcpy(head.data() + (MAPF_SMEM_CUM - MAPF_SMEM_IMG), ctx->pt.cum, sizeof(ctx->pt.cum));
+        memcpy(head.data() + (MAPF_SMEM_PP - MAPF_SMEM_IMG), ctx->pt.pp, sizeof(ctx->pt.pp));
+        memcpy(head.data() + (MAPF_SMEM_REW - MAPF_SMEM_IMG), ctx->pt.reward, sizeof(ctx->pt.reward));
+        uint16_t *act = reinterpret_cast<uint16_t *>(head.data() + (MAPF_SMEM_ACT - MAPF_SMEM_IMG));
+        for (u32 a = 0; a < 625; ++a) {  // base-5 digits of a four-agent joint action (__init__.py:26, mapf_env.py:101-102)
+            u32 x = a;
+            for (int j = 0; j < 4; ++j) { act[a * 4 + j] = (uint16_t)(act0 + (x % 5u) * 8u); x /= 5u; }
+        }
+        CTX_TRY(cudaMemcpy(ctx->d_image, head.data(), image_head, cudaMemcpyHostToDevice));
+        sp.image = ctx->d_image;
+        sp.image_bytes = (u32)(image_head + (luts ? lut_pad : 0));
+    }
     pick_kernels(n, sp.words, luts, &ctx->ks);
-    ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);
+    ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
     ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
     struct { const void *fn; size_t smem; int *grid; } plan[] = {
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
@@ -444,7 +493,7 @@ extern "C" int mapf_ctx_moves(const mapf_ctx *ctx, uint8_t *k, int32_t *dest, do
         if (k) k[i] = (uint8_t)kk;
         for (int j = 0; j < 3; ++j) {
             if (dest) dest[i * 3 + j] = j < kk ? (int32_t)((e >> (16 * j)) & 0xffffu) : -1;
-            if (prob) prob[i * 3 + j] = j < kk ? ctx->sp.pp[pid][j] : 0.0;
+            if (prob) prob[i * 3 + j] = j < kk ? ctx->pt.pp[pid][j] : 0.0;
         }
     }
     if (cells_rc)

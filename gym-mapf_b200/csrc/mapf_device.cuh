@@ -21,11 +21,14 @@ struct FastDiv {
     u32 shift;
     u32 pad;
 };
-// Division of any 32-bit x by L: q = umulhi(x, magic) >> shift underestimates by at most one (round-down magic),
-// which one compare fixes.
+// Division by L of a two-digit chunk x < L*L: q = umulhi(x, magic) >> shift.  For almost every L (all shipped maps)
+// a round-up magic exists that is exact on that range (fix == 0); otherwise a round-down magic underestimates by at
+// most one and one compare fixes it (fix == 1).
 struct Div32 {
     u32 magic;
     u32 shift;
+    u32 fix;
+    u32 pad;
 };
 
 // Move-table entry for one (cell, intended action): what `single_agent_movements` returns (mapf_env.py:163-184).
@@ -34,9 +37,17 @@ struct Div32 {
 //                                  left-slip} fell on the same cell.  It is the byte offset of the pattern's row in
 //                                  the per-pattern tables, whose probabilities are the candidates' added in list
 //                                  order (mapf_env.py:177-179)
-//   bits 56..57                    k = number of merged outcomes (1..3); bits 58..63 are zero
+//   bits 56..57                    k = number of merged outcomes (1..3)
+//   bits 58..62                    only on (cell, STAY) entries: bit 58 + i is set when the cell is agent i's goal
+//                                  (i < 5), i.e. agent i standing here and choosing STAY is "parked" under the
+//                                  sum-of-costs criterion (mapf_env.py:441-446); bit 63 is zero
 #define ENT_K(e) ((u32)((e) >> 56) & 3u)
 #define ENT_POFF(e) ((u32)((e) >> 48) & 0xffu)
+#define ENT_PARK_AGENTS 5
+#define ENT_PARK_SHIFT 58
+#define ENT_CORE(e) ((e) & 0x03ffffffffffffffull)  // without the parked bits
+// byte 6 of the entry (the pattern-row offset) from its high word, zero-extended: one PRMT
+__device__ __forceinline__ u32 ent_poff_hi(u32 ehi) { return __byte_perm(ehi, 0u, 0x4442); }
 // destination of merged outcome j (0..2): bytes 2j, 2j+1 of the entry, zero-extended.  The upper two selector
 // nibbles 0xF replicate the (always clear) sign bit of byte 7.
 __device__ __forceinline__ u32 ent_dest(u64 e, u32 j) {
@@ -63,11 +74,20 @@ struct DevSpec {
     Div32 divL;        // division by L of a two-digit chunk
     u64 s0[2];         // start state
     u64 sgoal[2];      // locations_to_state(agents_goals)
-    const u64 *lut;    // [L*5] move table, global memory
+    const u64 *lut;    // [L*5] move table, global memory (it lives inside `image`)
     u16 goal[16];      // goal cell per agent (mapf_env.py:158)
     u16 start[16];
-    // per merge pattern, for merged outcome j = 0..2 (slot 3 pads to 16 / 32 bytes):
-    u32 thr[MAPF_MAX_PATTERNS][8];     // ~T_j, T_j = largest 32-bit draw w with cumsum_j > w * 2**-32 (32-byte rows)
+    // Everything a hot CTA keeps in shared memory, laid out in global memory exactly as it sits there (see the
+    // MAPF_SMEM_* layout below), so that ONE bulk asynchronous copy per CTA stages it.
+    const unsigned char *image;
+    u32 image_bytes;   // multiple of 16; ends after the action table when the move table is not staged
+    u32 smem_window;   // shared-window address of a hot kernel's dynamic shared memory (probed at context creation;
+                       // the action table holds absolute shared-window addresses)
+};
+
+// Host-side staging of the per-pattern tables (one 32-byte row per merge pattern; slot 3 pads):
+struct PatternTables {
+    u32 thr[MAPF_MAX_PATTERNS][8];     // ~T_j, T_j = largest 32-bit draw w with cumsum_j > w * 2**-32
     double cum[MAPF_MAX_PATTERNS][4];  // np.cumsum of the merged probabilities (mapf_env.py:255)
     double pp[MAPF_MAX_PATTERNS][4];   // merged probabilities
     double reward[3 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living][parked agents]
@@ -81,7 +101,9 @@ __device__ __forceinline__ u64 fastdiv(u64 x, const FastDiv &d) {
 __device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &r) {
     q = __umulhi(x, sp.divL.magic) >> sp.divL.shift;
     r = x - q * (u32)sp.L;
-    if (r >= (u32)sp.L) { r -= (u32)sp.L; q += 1; }
+    if (sp.divL.fix) {  // kernel-uniform
+        if (r >= (u32)sp.L) { r -= (u32)sp.L; q += 1; }
+    }
 }
 
 // ---- joint state <-> per-agent cells: little-endian radix L, agent 0 least significant (__init__.py:50-79) ----
@@ -217,6 +239,22 @@ __device__ __forceinline__ int parked_agents(const DevSpec &sp, const int (&prev
     return k;
 }
 
+// The same count from the move-table entries of the agents' (cell, intended action): the first ENT_PARK_AGENTS
+// agents carry a "parked" bit in their entry, the others are compared.  `actv` holds action * 8 + act0.
+template <int N>
+__device__ __forceinline__ u32 parked_from_entries(const DevSpec &sp, u32 act0, const u32 (&ehi)[N], const int (&prev)[N],
+                                                   const u32 (&actv)[N]) {
+    u32 bits = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (i < ENT_PARK_AGENTS) bits |= ehi[i] & (1u << (ENT_PARK_SHIFT - 32 + i));
+    }
+    u32 k = __popc(bits);
+#pragma unroll
+    for (int i = ENT_PARK_AGENTS; i < N; ++i) k += ((((u32)prev[i] ^ (u32)sp.goal[i]) | (actv[i] ^ act0)) == 0u) ? 1u : 0u;
+    return k;
+}
+
 // (w > a) + (w > b) from the carry flag: w > a  <=>  w + ~a carries out of 32 bits.  The thresholds are stored
 // complemented (na = ~a, nb = ~b) so each comparison is one carry-generating add.
 __device__ __forceinline__ u32 count_below(u32 w, u32 na, u32 nb) {
@@ -264,24 +302,31 @@ __device__ __forceinline__ Philox4 philox_block(const PhiloxKeys &K, u64 env, u6
 
 // ---- shared memory: small per-pattern tables + the move table ------------------------------------------------
 // Layout of the dynamic shared memory of every hot kernel (pattern tables have one 32-byte row per pattern):
-//   [0, 256)       thr    u32[8][8]
-//   [256, 512)     cum    f64[8][4]
-//   [512, 768)     pp     f64[8][4]
-//   [768, 1152)    reward f64[48]
-//   [1152, 1168)   mbarrier of the bulk copy
-//   [1168 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
-#define MAPF_SMEM_THR 0
-#define MAPF_SMEM_CUM 256
-#define MAPF_SMEM_PP 512
-#define MAPF_SMEM_REW 768
-#define MAPF_SMEM_BAR 1152
-#define MAPF_SMEM_LUT 1168
+//   [0, 16)        mbarrier of the bulk copy
+//   [16, 272)      thr    u32[8][8]
+//   [272, 528)     cum    f64[8][4]
+//   [528, 784)     pp     f64[8][4]
+//   [784, 1168)    reward f64[48]
+//   [1168, 6176)   action table u16[625][4]: for a joint action of four agents (base-5 digits, agent 0 least
+//                  significant, __init__.py:26) the byte offsets action * 8 of their move-table entries, plus the
+//                  table's shared-window address when it is staged -- one LDS per agent replaces the divisions by 5
+//   [6176 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
+// Bytes [16, ...) are a verbatim copy of DevSpec::image.
+#define MAPF_SMEM_BAR 0
+#define MAPF_SMEM_IMG 16
+#define MAPF_SMEM_THR 16
+#define MAPF_SMEM_CUM 272
+#define MAPF_SMEM_PP 528
+#define MAPF_SMEM_REW 784
+#define MAPF_SMEM_ACT 1168
+#define MAPF_SMEM_LUT 6176
 
 // Shared memory is addressed through 32-bit shared-window addresses and explicit ld.shared, so that every table
 // access is one LDS with an immediate offset (no generic-address arithmetic).
 struct SmemTables {
     u32 base;          // shared-window address of the dynamic shared memory
     u32 lut;           // shared-window address of the staged move table
+    u32 act0;          // what the action table holds for STAY: the staged table's address, or 0
     const u64 *lut_g;  // the move table in global memory
 };
 
@@ -306,44 +351,33 @@ __device__ __forceinline__ uint2 lds_u32x2(u32 addr) {
     return v;
 }
 
-// Start staging: the small tables are written by the CTA's threads, the move table is fetched by ONE bulk
-// asynchronous copy (cp.async.bulk, the TMA engine) that completes on an mbarrier; compute that does not need
-// the table (loads, state decode, Philox) overlaps with it.  Call tables_wait() before the first table access.
+// Start staging: ONE thread issues the bulk asynchronous copy (cp.async.bulk, the TMA engine) of the whole image;
+// it completes on an mbarrier.  Compute that does not need the tables (global loads, state decode, Philox) overlaps
+// with it.  Call tables_wait() before the first table access.
 template <bool LUTS>
 __device__ __forceinline__ SmemTables tables_begin(const DevSpec &sp, unsigned char *smem) {
-    u32 *thr = reinterpret_cast<u32 *>(smem + MAPF_SMEM_THR);
-    double *cum = reinterpret_cast<double *>(smem + MAPF_SMEM_CUM);
-    double *pp = reinterpret_cast<double *>(smem + MAPF_SMEM_PP);
-    double *rw = reinterpret_cast<double *>(smem + MAPF_SMEM_REW);
-    u64 *bar = reinterpret_cast<u64 *>(smem + MAPF_SMEM_BAR);
-    unsigned char *lut_s = smem + MAPF_SMEM_LUT;
-    if (LUTS && threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
+    const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) != sp.smem_window) __trap();  // the action table was built for another window address
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = threadIdx.x; i < MAPF_MAX_PATTERNS * 8; i += blockDim.x) thr[i] = (&sp.thr[0][0])[i];
-    for (int i = threadIdx.x; i < MAPF_MAX_PATTERNS * 4; i += blockDim.x) {
-        cum[i] = (&sp.cum[0][0])[i];
-        pp[i] = (&sp.pp[0][0])[i];
-    }
-    for (int i = threadIdx.x; i < 3 * MAPF_REW_STRIDE; i += blockDim.x) rw[i] = sp.reward[i];
-    __syncthreads();
-    if (LUTS && threadIdx.x == 0) {
-        const u32 bytes = sp.lut_bytes;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        const u32 bytes = sp.image_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         u32 off = 0;
         while (off < bytes) {  // pieces of at most 32 KiB
             const u32 piece = bytes - off < 32768u ? bytes - off : 32768u;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             smem_u32(lut_s + off)),
-                         "l"(reinterpret_cast<const unsigned char *>(sp.lut) + off), "r"(piece), "r"(smem_u32(bar))
+                             smem_u32(smem + MAPF_SMEM_IMG + off)),
+                         "l"(sp.image + off), "r"(piece), "r"(bar)
                          : "memory");
             off += piece;
         }
     }
+    __syncthreads();  // the initialised barrier is visible to every thread before it polls
     SmemTables t;
     t.base = smem_u32(smem);
-    t.lut = smem_u32(lut_s);
+    t.lut = smem_u32(smem + MAPF_SMEM_LUT);
+    t.act0 = LUTS ? t.lut : 0u;
     asm volatile("" : "+r"(t.base), "+r"(t.lut));  // opaque: keep both in registers instead of re-deriving them
     t.lut_g = sp.lut;
     return t;
@@ -351,16 +385,41 @@ __device__ __forceinline__ SmemTables tables_begin(const DevSpec &sp, unsigned c
 
 template <bool LUTS>
 __device__ __forceinline__ void tables_wait(unsigned char *smem) {
-    if (LUTS) {
-        const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
-        u32 ok;
-        do {
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ok)
-                         : "r"(bar), "r"(0u)
-                         : "memory");
-        } while (!ok);
+    const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
+    u32 ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(0u)
+                     : "memory");
+    } while (!ok);
+}
+
+template <int OFF>
+__device__ __forceinline__ u32 lds_u16(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// Joint action -> per agent `action * 8 (+ the staged move table's address)`, straight from the action table.
+template <int N>
+__device__ __forceinline__ void load_actions(const DevSpec &sp, const SmemTables &tb, u32 a, u32 (&actv)[N]) {
+    a = min(a, (u32)sp.nA - 1u);  // an invalid action (rejected by the host API) must not index outside the table
+#pragma unroll
+    for (int c = 0; c < (N + 3) / 4; ++c) {
+        u32 idx = a;
+        if (c + 1 < (N + 3) / 4) {
+            const u32 q = __umulhi(a, 0x68DB8BADu) >> 8;  // a / 625, exact for a < 2**31 (nA <= 5**13)
+            idx = a - q * 625u;
+            a = q;
+        }
+        const u32 addr = tb.base + idx * 8u;
+        if (4 * c + 0 < N) actv[4 * c + 0] = lds_u16<MAPF_SMEM_ACT + 0>(addr);
+        if (4 * c + 1 < N) actv[4 * c + 1] = lds_u16<MAPF_SMEM_ACT + 2>(addr);
+        if (4 * c + 2 < N) actv[4 * c + 2] = lds_u16<MAPF_SMEM_ACT + 4>(addr);
+        if (4 * c + 3 < N) actv[4 * c + 3] = lds_u16<MAPF_SMEM_ACT + 6>(addr);
     }
 }
 

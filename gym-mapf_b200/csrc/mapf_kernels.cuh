@@ -91,8 +91,20 @@ __device__ __forceinline__ u64 bm_entry(const BitmapView &bm, int r, int c, int 
     return (u64)dest[0] | ((u64)dest[1] << 16) | ((u64)dest[2] << 32) | ((u64)(pid * 32u) << 48) | ((u64)k << 56);
 }
 
+// shared-window address of a kernel's dynamic shared memory (context creation; see DevSpec::smem_window)
+static __global__ void k_probe_smem(u32 *out) {
+    extern __shared__ __align__(16) unsigned char probe_smem[];
+    if (threadIdx.x == 0) *out = smem_u32(probe_smem);
+}
+
+struct GoalList {
+    u16 cell[16];
+    int n;
+};
+
 static __global__ void k_build_moves(const u32 *__restrict__ colbits, const u32 *__restrict__ colbase, int H, int W, int wpc,
-                              int cand_mask, PatternList pats, u64 *__restrict__ lut, u32 *__restrict__ cell_rc) {
+                              int cand_mask, PatternList pats, GoalList goals, u64 *__restrict__ lut,
+                              u32 *__restrict__ cell_rc) {
     extern __shared__ u32 bm_smem[];
     u32 *s_bits = bm_smem;
     u32 *s_base = bm_smem + W * wpc;
@@ -105,7 +117,10 @@ static __global__ void k_build_moves(const u32 *__restrict__ colbits, const u32 
         if (!bm_free(bm, r, c)) continue;
         int id = bm_rank(bm, r, c);
         cell_rc[id] = ((u32)r << 16) | (u32)c;
-        for (int a = 0; a < 5; ++a) lut[id * 5 + a] = bm_entry(bm, r, c, a, cand_mask, pats);
+        u64 parked = 0;  // STAY on this cell parks agent i when it is agent i's goal (mapf_env.py:441-446)
+        for (int i = 0; i < goals.n && i < ENT_PARK_AGENTS; ++i)
+            if ((int)goals.cell[i] == id) parked |= 1ull << (ENT_PARK_SHIFT + i);
+        for (int a = 0; a < 5; ++a) lut[id * 5 + a] = bm_entry(bm, r, c, a, cand_mask, pats) | (a == 0 ? parked : 0ull);
     }
 }
 
@@ -419,6 +434,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
+                ent[i] = ENT_CORE(ent[i]);  // phase B reads k as e >> 56
                 sl.ent[i][lane] = ent[i];
                 sl.prev[i][lane] = (u16)cell[i];
                 const u32 k = ENT_K(ent[i]);
@@ -558,7 +574,7 @@ k_checksum(int words, i64 n, i64 index_base, const u64 *__restrict__ next_state,
 template <int N>
 struct EnvIn {
     int cell[N];
-    int act[N];
+    u32 actv[N];               // intended action * 8 (+ the staged move table's address): see load_actions()
     u32 w[((N + 3) / 4) * 4];  // Philox words, one per agent
     u64 lo, hi;
 };
@@ -589,11 +605,12 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
                                            const double *__restrict__ u, u32 opts, int (&nxt)[N]) {
     double total;
     const bool term = is_terminal<N>(sp, in.cell, in.lo, in.hi);
-    const u32 act_base = LUTS ? tb.lut : 0u;
+    u32 ehi[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const u64 e = lut_entry<LUTS>(tb, (u32)in.cell[i], (u32)in.act[i] * 8u + act_base);
-        const u32 row = tb.base + ENT_POFF(e);
+        const u64 e = lut_entry<LUTS>(tb, (u32)in.cell[i], in.actv[i]);
+        ehi[i] = (u32)(e >> 32);
+        const u32 row = tb.base + ent_poff_hi(ehi[i]);
         u32 pick;
         if (TAPE) {
             const double ui = u[i];
@@ -614,7 +631,9 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
     encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
     const bool goal = out.lo == sp.sgoal[0] && out.hi == sp.sgoal[1];  // every agent on its goal
     const int kind = clash ? 1 : (goal ? 2 : 0);
-    out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + parked_agents<N>(sp, in.cell, in.act)) * 8u);
+    // living reward: Makespan rows of the table hold the same value for every parked count
+    out.reward = lds_f64<MAPF_SMEM_REW>(
+        tb.base + ((u32)(kind * MAPF_REW_STRIDE) + parked_from_entries<N>(sp, tb.act0, ehi, in.cell, in.actv)) * 8u);
     out.prob = total;
     out.done = kind != 0 ? 1u : 0u;
     out.coll = clash ? 1u : 0u;
@@ -686,8 +705,8 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         for (int q = 0; q < EPT; ++q) {
             in[q].lo = raw.lo[q];
             in[q].hi = raw.hi[q];
-            decode_action<N>(raw.a[q], in[q].act);
         }
+        const u32 a_raw[2] = {raw.a[0], raw.a[EPT - 1]};
         const u32 it_next = it + stride;
         if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
 #pragma unroll
@@ -699,6 +718,7 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         EnvOut o[EPT];
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
+            load_actions<N>(sp, tb, a_raw[q], in[q].actv);
             int nxt[N];
             o[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (size_t)(b + q) * N : nullptr, opts,
                                                   nxt);
@@ -742,9 +762,9 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
             const i64 o = t * (i64)B + b;
             const u64 env = env0 + (u64)b, stp = step0 + (u64)t;
             const u32 a = actions ? (u32)actions[o] : random_action(sp, keys, env, stp);
-            decode_action<N>(a, in.act);
             if (!TAPE) env_draws<N>(keys, env, stp, in);
             if (!ready) { tables_wait<LUTS>(smem); ready = true; }
+            load_actions<N>(sp, tb, a, in.actv);
             int nxt[N];
             EnvOut r = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in, TAPE ? uniforms + o * N : nullptr, opts, nxt);
             store_state<WORDS>(next_states, o, r.lo, r.hi);
