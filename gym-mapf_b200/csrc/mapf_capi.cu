@@ -334,6 +334,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         ctx->pt.reward[0 * MAPF_REW_STRIDE + k] = live;
         ctx->pt.reward[1 * MAPF_REW_STRIDE + k] = spec->reward_of_clash + live;
         ctx->pt.reward[2 * MAPF_REW_STRIDE + k] = spec->reward_of_goal + live;
+        ctx->pt.reward[3 * MAPF_REW_STRIDE + k] = 0.0;  // step from a terminal state (mapf_env.py:240)
     }
 
     // ---- device side

@@ -90,7 +90,7 @@ struct PatternTables {
     u32 thr[MAPF_MAX_PATTERNS][8];     // ~T_j, T_j = largest 32-bit draw w with cumsum_j > w * 2**-32
     double cum[MAPF_MAX_PATTERNS][4];  // np.cumsum of the merged probabilities (mapf_env.py:255)
     double pp[MAPF_MAX_PATTERNS][4];   // merged probabilities
-    double reward[3 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living][parked agents]
+    double reward[4 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living, 3: terminal state = 0][parked agents]
 };
 
 __device__ __forceinline__ u64 fastdiv(u64 x, const FastDiv &d) {
@@ -265,6 +265,9 @@ __device__ __forceinline__ u32 count_below(u32 w, u32 na, u32 nb) {
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), the counter-based generator of the device-side sampling mode -------
+#ifndef MAPF_PHILOX_ROUNDS
+#define MAPF_PHILOX_ROUNDS 10  // experiments only: anything else changes the stream
+#endif
 struct Philox4 {
     u32 v[4];
 };
@@ -275,7 +278,7 @@ struct PhiloxKeys {
 };
 __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const PhiloxKeys &K) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < MAPF_PHILOX_ROUNDS; ++r) {
 #ifndef MAPF_PHILOX_NARROW  // one wide multiply per product (measured faster than separate hi/lo multiplies)
         u64 p0, p1;
         asm("mul.wide.u32 %0, %1, %2;" : "=l"(p0) : "r"(c0), "r"(0xD2511F53u));
@@ -306,11 +309,11 @@ __device__ __forceinline__ Philox4 philox_block(const PhiloxKeys &K, u64 env, u6
 //   [16, 272)      thr    u32[8][8]
 //   [272, 528)     cum    f64[8][4]
 //   [528, 784)     pp     f64[8][4]
-//   [784, 1168)    reward f64[48]
-//   [1168, 6176)   action table u16[625][4]: for a joint action of four agents (base-5 digits, agent 0 least
+//   [784, 1296)    reward f64[64]: rows living, clash + living, goal + living, terminal state (zeros)
+//   [1296, 6304)   action table u16[625][4]: for a joint action of four agents (base-5 digits, agent 0 least
 //                  significant, __init__.py:26) the byte offsets action * 8 of their move-table entries, plus the
 //                  table's shared-window address when it is staged -- one LDS per agent replaces the divisions by 5
-//   [6176 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
+//   [6304 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
 // Bytes [16, ...) are a verbatim copy of DevSpec::image.
 #define MAPF_SMEM_BAR 0
 #define MAPF_SMEM_IMG 16
@@ -318,8 +321,8 @@ __device__ __forceinline__ Philox4 philox_block(const PhiloxKeys &K, u64 env, u6
 #define MAPF_SMEM_CUM 272
 #define MAPF_SMEM_PP 528
 #define MAPF_SMEM_REW 784
-#define MAPF_SMEM_ACT 1168
-#define MAPF_SMEM_LUT 6176
+#define MAPF_SMEM_ACT 1296
+#define MAPF_SMEM_LUT 6304
 
 // Shared memory is addressed through 32-bit shared-window addresses and explicit ld.shared, so that every table
 // access is one LDS with an immediate offset (no generic-address arithmetic).
@@ -406,6 +409,15 @@ __device__ __forceinline__ u32 lds_u16(u32 addr) {
 // Joint action -> per agent `action * 8 (+ the staged move table's address)`, straight from the action table.
 template <int N>
 __device__ __forceinline__ void load_actions(const DevSpec &sp, const SmemTables &tb, u32 a, u32 (&actv)[N]) {
+#if defined(MAPF_ACTION_ARITH)  // experiment: base-5 digits by multiply-high instead of the shared-memory table
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const u32 q = a / 5u;
+        actv[i] = (a - q * 5u) * 8u + tb.act0;
+        a = q;
+    }
+    return;
+#endif
     a = min(a, (u32)sp.nA - 1u);  // an invalid action (rejected by the host API) must not index outside the table
 #pragma unroll
     for (int c = 0; c < (N + 3) / 4; ++c) {

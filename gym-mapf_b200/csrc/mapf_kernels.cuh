@@ -9,6 +9,9 @@
 #pragma once
 #include "mapf_device.cuh"
 
+#ifndef MAPF_ABLATE
+#define MAPF_ABLATE 0  // timing experiments only (tools/sweep8.sh); 0 = the real kernel
+#endif
 #ifndef MAPF_MAX_THREADS
 #define MAPF_MAX_THREADS 512  // largest CTA the hot kernels are launched with
 #endif
@@ -608,7 +611,11 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
     u32 ehi[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+#if MAPF_ABLATE == 1  // experiment: no move-table gather (a made-up entry keeps the data flow alive)
+        const u64 e = ((u64)in.cell[i] * 0x0001000100010001ull + in.actv[i]) & 0x0000ffffffffffffull;
+#else
         const u64 e = lut_entry<LUTS>(tb, (u32)in.cell[i], in.actv[i]);
+#endif
         ehi[i] = (u32)(e >> 32);
         const u32 row = tb.base + ent_poff_hi(ehi[i]);
         u32 pick;
@@ -623,22 +630,26 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
             pick = count_below(w, t.x, t.y);
         }
         nxt[i] = (int)ent_dest(e, pick);
-        const double pi = lds_f64<MAPF_SMEM_PP>(row + pick * 8u);
+        // a terminal state's probability is 0 (mapf_env.py:240): its first factor is the zero that pads every row
+        const u32 pslot = (i == 0 && term) ? 24u : pick * 8u;
+        const double pi = lds_f64<MAPF_SMEM_PP>(row + pslot);
         total = i == 0 ? pi : __dmul_rn(total, pi);  // 1 * p0 * p1 * ... (mapf_env.py:250,257)
     }
     const bool clash = has_clash<N>(in.cell, nxt);
     EnvOut out;
     encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
     const bool goal = out.lo == sp.sgoal[0] && out.hi == sp.sgoal[1];  // every agent on its goal
-    const int kind = clash ? 1 : (goal ? 2 : 0);
+    // row of the reward table: 0 living, 1 clash (beats goal, mapf_env.py:228-233), 2 goal, 3 terminal state =
+    // (s, 0, True, {"prob": 0}) (mapf_env.py:238-240), a no-op that consumes no draw
+    const int kind = term ? 3 : (clash ? 1 : (goal ? 2 : 0));
     // living reward: Makespan rows of the table hold the same value for every parked count
     out.reward = lds_f64<MAPF_SMEM_REW>(
         tb.base + ((u32)(kind * MAPF_REW_STRIDE) + parked_from_entries<N>(sp, tb.act0, ehi, in.cell, in.actv)) * 8u);
     out.prob = total;
     out.done = kind != 0 ? 1u : 0u;
-    out.coll = clash ? 1u : 0u;
-    if (term) {  // (s, 0, True, {"prob": 0})  (mapf_env.py:238-240): a no-op that consumes no draw
-        out.lo = in.lo; out.hi = in.hi; out.reward = 0.0; out.prob = 0.0; out.done = 1u; out.coll = 0u;
+    out.coll = kind == 1 ? 1u : 0u;
+    if (term) {
+        out.lo = in.lo; out.hi = in.hi;
 #pragma unroll
         for (int i = 0; i < N; ++i) nxt[i] = in.cell[i];
     }
@@ -708,7 +719,11 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         }
         const u32 a_raw[2] = {raw.a[0], raw.a[EPT - 1]};
         const u32 it_next = it + stride;
+#if MAPF_ABLATE == 4  // experiment: no global loads after the first
+        if (it_next < n_items) { raw.lo[0] += it_next; raw.lo[EPT - 1] += 2 * it_next; raw.a[0] = (raw.a[0] + 7u) % 625u; }
+#else
         if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
+#endif
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             decode_state<N, WORDS>(sp, in[q].lo, in[q].hi, in[q].cell);
@@ -723,6 +738,9 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
             o[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (size_t)(b + q) * N : nullptr, opts,
                                                   nxt);
         }
+#if MAPF_ABLATE == 3  // experiment: almost no stores (the condition is never true, but the compiler cannot know)
+        if (o[0].prob < -1.0)
+#endif
         if (EPT == 2) {
             if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
             else {
