@@ -430,6 +430,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         memcpy(head.data() + (MAPF_SMEM_THR - MAPF_SMEM_IMG), ctx->pt.thr, sizeof(ctx->pt.thr));
         memcpy(head.data() + (MAPF_SMEM_CUM - MAPF_SMEM_IMG), ctx->pt.cum, sizeof(ctx->pt.cum));
         memcpy(head.data() + (MAPF_SMEM_PP - MAPF_SMEM_IMG), ctx->pt.pp, sizeof(ctx->pt.pp));
+        memcpy(head.data() + (MAPF_SMEM_PZERO - MAPF_SMEM_IMG), ctx->pt.zero, sizeof(ctx->pt.zero));
         memcpy(head.data() + (MAPF_SMEM_REW - MAPF_SMEM_IMG), ctx->pt.reward, sizeof(ctx->pt.reward));
         uint16_t *act = reinterpret_cast<uint16_t *>(head.data() + (MAPF_SMEM_ACT - MAPF_SMEM_IMG));
         for (u32 a = 0; a < 625; ++a) {  // base-5 digits of a four-agent joint action (__init__.py:26, mapf_env.py:101-102)
@@ -490,7 +491,7 @@ extern "C" int mapf_ctx_moves(const mapf_ctx *ctx, uint8_t *k, int32_t *dest, do
     for (int i = 0; i < L * 5; ++i) {
         const u64 e = ctx->h_lut[i];
         const int kk = (int)ENT_K(e);
-        const u32 pid = ENT_POFF(e) / 32u;
+        const u32 pid = ENT_POFF(e) / MAPF_PAT_STRIDE;
         if (k) k[i] = (uint8_t)kk;
         for (int j = 0; j < 3; ++j) {
             if (dest) dest[i * 3 + j] = j < kk ? (int32_t)((e >> (16 * j)) & 0xffffu) : -1;
@@ -782,6 +783,39 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
     DeviceGuard g(ctx->device);
     const int n = ctx->sp.n;
     const size_t sw = (size_t)ctx->sp.words * 8;
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+    // Zero-copy path: when every buffer is page-locked host memory that the device can address (cudaHostAlloc /
+    // cudaHostRegister, e.g. torch's pin_memory()), ONE launch of the step kernel reads the inputs and writes the
+    // results straight over PCIe -- both directions stream concurrently, with no staging copies and no per-copy
+    // driver calls.  Otherwise fall back to staged copies below.
+    {
+        const void *host_in[3] = {states, actions, uniforms};
+        void *host_out[5] = {next_states, reward, prob, done, collision};
+        void *dev_in[3] = {nullptr, nullptr, nullptr}, *dev_out[5];
+        bool mapped = getenv("MAPF_HOST_STAGED") == nullptr;
+        for (int i = 0; i < 3 && mapped; ++i) {
+            if (!host_in[i]) continue;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host_in[i]) != cudaSuccess || at.type != cudaMemoryTypeHost ||
+                !at.devicePointer) { cudaGetLastError(); mapped = false; break; }
+            dev_in[i] = at.devicePointer;
+        }
+        for (int i = 0; i < 5 && mapped; ++i) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host_out[i]) != cudaSuccess || at.type != cudaMemoryTypeHost ||
+                !at.devicePointer) { cudaGetLastError(); mapped = false; break; }
+            dev_out[i] = at.devicePointer;
+        }
+        if (mapped) {
+            int rc = launch_step(ctx, dev_in[0], (const int32_t *)dev_in[1], B, (const double *)dev_in[2], seed, step_index,
+                                 env_offset, options, dev_out[0], (double *)dev_out[1], (double *)dev_out[2],
+                                 (uint8_t *)dev_out[3], (uint8_t *)dev_out[4], ctx->hs[0]);
+            if (rc) return rc;
+            CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
+            return MAPF_OK;
+        }
+    }
     // per-env device bytes: state in, action, uniforms, state out, reward, prob, done, collision
     const size_t per_env = sw + 4 + (uniforms ? (size_t)n * 8 : 0) + sw + 8 + 8 + 1 + 1;
     const size_t need = per_env * (size_t)B + 8 * 256;
@@ -792,8 +826,6 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         CUDA_TRY(cudaMalloc(&ctx->d_stage, need));
         ctx->d_stage_bytes = need;
     }
-    for (int i = 0; i < 2; ++i)
-        if (!ctx->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
     auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
     unsigned char *p = ctx->d_stage;
     unsigned char *d_s = p; p += align(sw * B);

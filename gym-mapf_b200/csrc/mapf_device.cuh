@@ -13,6 +13,7 @@ typedef unsigned char u8;
 #define MAPF_MAXN 13
 #define MAPF_REW_STRIDE 16  // reward table row: parked-agent count 0..13
 #define MAPF_MAX_PATTERNS 8
+#define MAPF_PAT_STRIDE 24  // bytes per pattern row: 5 rows of 24 B fall on disjoint shared-memory banks (32 B rows wrap)
 
 // Exact unsigned 64-bit division by a run-time constant d >= 1, branch-free (Granlund-Montgomery round-up method
 // with the 65-bit magic; a power of two uses magic 0): q = mulhi(x, magic); q = (((x - q) >> 1) + q) >> shift.
@@ -33,7 +34,7 @@ struct Div32 {
 
 // Move-table entry for one (cell, intended action): what `single_agent_movements` returns (mapf_env.py:163-184).
 //   bits  0..15 / 16..31 / 32..47  destination cell of merged outcome 0 / 1 / 2 (unused slots repeat slot 0)
-//   bits 48..55                    32 * merge pattern id: which of the candidates {intended, right-slip,
+//   bits 48..55                    24 * merge pattern id: which of the candidates {intended, right-slip,
 //                                  left-slip} fell on the same cell.  It is the byte offset of the pattern's row in
 //                                  the per-pattern tables, whose probabilities are the candidates' added in list
 //                                  order (mapf_env.py:177-179)
@@ -85,12 +86,13 @@ struct DevSpec {
                        // the action table holds absolute shared-window addresses)
 };
 
-// Host-side staging of the per-pattern tables (one 32-byte row per merge pattern; slot 3 pads):
+// Host-side staging of the per-pattern tables (one MAPF_PAT_STRIDE-byte row per merge pattern):
 struct PatternTables {
-    u32 thr[MAPF_MAX_PATTERNS][8];     // ~T_j, T_j = largest 32-bit draw w with cumsum_j > w * 2**-32
-    double cum[MAPF_MAX_PATTERNS][4];  // np.cumsum of the merged probabilities (mapf_env.py:255)
-    double pp[MAPF_MAX_PATTERNS][4];   // merged probabilities
-    double reward[4 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living, 3: terminal state = 0][parked agents]
+    u32 thr[MAPF_MAX_PATTERNS][6];     // ~T_j (j = 0, 1, 2), T_j = largest 32-bit draw w with cumsum_j > w * 2**-32
+    double cum[MAPF_MAX_PATTERNS][3];  // np.cumsum of the merged probabilities (mapf_env.py:255)
+    double pp[MAPF_MAX_PATTERNS][3];   // merged probabilities
+    double zero[2];                    // 0.0: the probability factor of a step from a terminal state
+    double reward[4 * MAPF_REW_STRIDE];  // [0: living, 1: clash + living, 2: goal + living, 3: terminal = 0][parked agents]
 };
 
 __device__ __forceinline__ u64 fastdiv(u64 x, const FastDiv &d) {
@@ -306,23 +308,26 @@ __device__ __forceinline__ Philox4 philox_block(const PhiloxKeys &K, u64 env, u6
 // ---- shared memory: small per-pattern tables + the move table ------------------------------------------------
 // Layout of the dynamic shared memory of every hot kernel (pattern tables have one 32-byte row per pattern):
 //   [0, 16)        mbarrier of the bulk copy
-//   [16, 272)      thr    u32[8][8]
-//   [272, 528)     cum    f64[8][4]
-//   [528, 784)     pp     f64[8][4]
-//   [784, 1296)    reward f64[64]: rows living, clash + living, goal + living, terminal state (zeros)
-//   [1296, 6304)   action table u16[625][4]: for a joint action of four agents (base-5 digits, agent 0 least
+//   [16, 208)      thr    u32[8][6]
+//   [208, 400)     cum    f64[8][3]
+//   [400, 592)     pp     f64[8][3]
+//   [592, 608)     0.0
+//   [608, 1120)    reward f64[64]: rows living, clash + living, goal + living, terminal state (zeros)
+//   [1120, 6128)   action table u16[625][4]: for a joint action of four agents (base-5 digits, agent 0 least
 //                  significant, __init__.py:26) the byte offsets action * 8 of their move-table entries, plus the
-//                  table's shared-window address when it is staged -- one LDS per agent replaces the divisions by 5
-//   [6304 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
+//                  table's shared-window address when it is staged -- one 8-byte load per four agents replaces the
+//                  divisions by 5
+//   [6128 ...)     move table u64[L*5] (when staged), then kernel-specific scratch
 // Bytes [16, ...) are a verbatim copy of DevSpec::image.
 #define MAPF_SMEM_BAR 0
 #define MAPF_SMEM_IMG 16
 #define MAPF_SMEM_THR 16
-#define MAPF_SMEM_CUM 272
-#define MAPF_SMEM_PP 528
-#define MAPF_SMEM_REW 784
-#define MAPF_SMEM_ACT 1296
-#define MAPF_SMEM_LUT 6304
+#define MAPF_SMEM_CUM 208
+#define MAPF_SMEM_PP 400
+#define MAPF_SMEM_PZERO 592
+#define MAPF_SMEM_REW 608
+#define MAPF_SMEM_ACT 1120
+#define MAPF_SMEM_LUT 6128
 
 // Shared memory is addressed through 32-bit shared-window addresses and explicit ld.shared, so that every table
 // access is one LDS with an immediate offset (no generic-address arithmetic).
@@ -427,11 +432,11 @@ __device__ __forceinline__ void load_actions(const DevSpec &sp, const SmemTables
             idx = a - q * 625u;
             a = q;
         }
-        const u32 addr = tb.base + idx * 8u;
-        if (4 * c + 0 < N) actv[4 * c + 0] = lds_u16<MAPF_SMEM_ACT + 0>(addr);
-        if (4 * c + 1 < N) actv[4 * c + 1] = lds_u16<MAPF_SMEM_ACT + 2>(addr);
-        if (4 * c + 2 < N) actv[4 * c + 2] = lds_u16<MAPF_SMEM_ACT + 4>(addr);
-        if (4 * c + 3 < N) actv[4 * c + 3] = lds_u16<MAPF_SMEM_ACT + 6>(addr);
+        const uint2 v = lds_u32x2<MAPF_SMEM_ACT>(tb.base + idx * 8u);  // ONE load: four 16-bit values
+        if (4 * c + 0 < N) actv[4 * c + 0] = v.x & 0xffffu;
+        if (4 * c + 1 < N) actv[4 * c + 1] = v.x >> 16;
+        if (4 * c + 2 < N) actv[4 * c + 2] = v.y & 0xffffu;
+        if (4 * c + 3 < N) actv[4 * c + 3] = v.y >> 16;
     }
 }
 

@@ -91,7 +91,7 @@ __device__ __forceinline__ u64 bm_entry(const BitmapView &bm, int r, int c, int 
     u32 pid = 0;
     for (int q = 0; q < pats.count; ++q)
         if (pats.triple[q] == triple) pid = (u32)q;
-    return (u64)dest[0] | ((u64)dest[1] << 16) | ((u64)dest[2] << 32) | ((u64)(pid * 32u) << 48) | ((u64)k << 56);
+    return (u64)dest[0] | ((u64)dest[1] << 16) | ((u64)dest[2] << 32) | ((u64)(pid * MAPF_PAT_STRIDE) << 48) | ((u64)k << 56);
 }
 
 // shared-window address of a kernel's dynamic shared memory (context creation; see DevSpec::smem_window)
@@ -630,9 +630,9 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
             pick = count_below(w, t.x, t.y);
         }
         nxt[i] = (int)ent_dest(e, pick);
-        // a terminal state's probability is 0 (mapf_env.py:240): its first factor is the zero that pads every row
-        const u32 pslot = (i == 0 && term) ? 24u : pick * 8u;
-        const double pi = lds_f64<MAPF_SMEM_PP>(row + pslot);
+        // a terminal state's probability is 0 (mapf_env.py:240): its first factor is the 0.0 behind the tables
+        const u32 paddr = (i == 0 && term) ? tb.base + (MAPF_SMEM_PZERO - MAPF_SMEM_PP) : row + pick * 8u;
+        const double pi = lds_f64<MAPF_SMEM_PP>(paddr);
         total = i == 0 ? pi : __dmul_rn(total, pi);  // 1 * p0 * p1 * ... (mapf_env.py:250,257)
     }
     const bool clash = has_clash<N>(in.cell, nxt);

@@ -310,3 +310,49 @@ def test_errors_and_edge_cases(torch):
                               torch.from_numpy(a.astype(np.int32)).to(eng.torch_device))
         assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
                           G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+
+
+@pytest.mark.parametrize("name", ["rows_c2", "rows_c4"])
+def test_step_host_zero_copy_and_staged(name, torch):
+    """mapf_step_host: pinned host buffers take the zero-copy path (the kernel reads/writes host memory over PCIe),
+    pageable numpy buffers the staged-copy path; both must equal the oracle on the same uniforms, and the Philox mode
+    must equal the device-buffer step."""
+    spec, _ = G.load(name)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    B, n = 70001, eng.n
+    rng = np.random.default_rng(21)
+    cells = rng.integers(0, eng.L, (B, n)).astype(np.int32)
+    lo, hi = ora.encode(cells)
+    actions = rng.integers(0, eng.nA, B).astype(np.int32)
+    uniforms = rng.random((B, n))
+    want = ora.step(lo, hi, actions.astype(np.int64), uniforms)
+    host_states = states_tensor(eng, lo, hi).cpu()
+
+    def outputs(pinned):
+        out = (torch.empty(eng.state_shape(B), dtype=torch.int64), torch.empty(B, dtype=torch.float64),
+               torch.empty(B, dtype=torch.float64), torch.empty(B, dtype=torch.bool), torch.empty(B, dtype=torch.bool))
+        return tuple(t.pin_memory() for t in out) if pinned else out
+
+    for pinned in (True, False):
+        st = host_states.pin_memory() if pinned else host_states.clone()
+        ac = torch.from_numpy(actions)
+        un = torch.from_numpy(uniforms)
+        if pinned:
+            ac, un = ac.pin_memory(), un.pin_memory()
+        out = outputs(pinned)
+        eng.step_host(st, ac, out, uniforms=un)
+        ns = out[0].numpy().view(np.uint64)
+        glo, ghi = (ns, np.zeros_like(ns)) if eng.words == 1 else (ns[:, 0], ns[:, 1])
+        assert np.array_equal(glo, want["next_lo"]) and np.array_equal(ghi, want["next_hi"]), pinned
+        assert np.array_equal(out[1].numpy().view(np.uint64), G.f64_to_bits(want["reward"]))
+        assert np.array_equal(out[2].numpy().view(np.uint64), G.f64_to_bits(want["prob"]))
+        assert np.array_equal(out[3].numpy().astype(np.uint8), want["done"])
+        assert np.array_equal(out[4].numpy().astype(np.uint8), want["collision"])
+        # device-side sampling: host path == device path
+        out2 = outputs(pinned)
+        eng.step_host(st, ac, out2, seed=99, step_index=5, env_offset=123)
+        dev = eng.step(states_tensor(eng, lo, hi), torch.from_numpy(actions).to(eng.torch_device), seed=99, step_index=5,
+                       env_offset=123)
+        assert np.array_equal(out2[0].numpy(), dev[0].cpu().numpy())
+        assert np.array_equal(out2[2].numpy().view(np.uint64), u64(dev[2]))
