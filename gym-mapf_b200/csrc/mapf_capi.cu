@@ -410,7 +410,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         const int t = atoi(e);
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
     }
-    const bool luts = MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.expand_slab_bytes <= smem_limit;
+    const bool luts = sp.divL.fix == 0 &&
+                      MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.expand_slab_bytes <= smem_limit;
     if (!luts) ctx->threads = 256;
     sp.lut_smem = luts ? 1 : 0;
     {

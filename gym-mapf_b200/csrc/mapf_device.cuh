@@ -99,11 +99,13 @@ __device__ __forceinline__ u64 fastdiv(u64 x, const FastDiv &d) {
     const u64 q = __umul64hi(x, d.magic);
     return (((x - q) >> 1) + q) >> d.shift;
 }
-// chunk -> (chunk % L, chunk / L)
+// chunk -> (chunk % L, chunk / L).  EXACT: the context guarantees an exact magic (Div32::fix == 0), which holds
+// whenever the move table is staged in shared memory (every L below 52186 has one); the correction is compiled out.
+template <bool EXACT>
 __device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &r) {
     q = __umulhi(x, sp.divL.magic) >> sp.divL.shift;
     r = x - q * (u32)sp.L;
-    if (sp.divL.fix) {  // kernel-uniform
+    if (!EXACT && sp.divL.fix) {
         if (r >= (u32)sp.L) { r -= (u32)sp.L; q += 1; }
     }
 }
@@ -111,7 +113,7 @@ __device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &
 // ---- joint state <-> per-agent cells: little-endian radix L, agent 0 least significant (__init__.py:50-79) ----
 // The state is split into two-digit chunks (radix L*L < 2**32) with 64-bit divisions and each chunk into its two
 // digits with one 32-bit multiply-high division.
-template <int N, int WORDS>
+template <int N, int WORDS, bool EXACT = false>
 __device__ __forceinline__ void decode_state(const DevSpec &sp, u64 lo, u64 hi, int (&cell)[N]) {
     constexpr int PAIRS = (N + 1) / 2;
     u32 chunk[PAIRS];
@@ -154,7 +156,7 @@ __device__ __forceinline__ void decode_state(const DevSpec &sp, u64 lo, u64 hi, 
     for (int p = 0; p < PAIRS; ++p) {
         if (2 * p + 1 < N) {
             u32 q, r;
-            divmod_L(sp, chunk[p], q, r);
+            divmod_L<EXACT>(sp, chunk[p], q, r);
             cell[2 * p] = (int)r;
             cell[2 * p + 1] = (int)q;
         } else {

@@ -429,7 +429,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, slo, shi, a);
             int cell[N], act[N];
             u64 ent[N];
-            decode_state<N, WORDS>(sp, slo, shi, cell);
+            decode_state<N, WORDS, LUTS>(sp, slo, shi, cell);
             decode_action<N>(a, act);
             const bool term = is_terminal<N>(sp, cell, slo, shi);
             len = 1;
@@ -726,7 +726,7 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
 #endif
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
-            decode_state<N, WORDS>(sp, in[q].lo, in[q].hi, in[q].cell);
+            decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
             if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step, in[q]);
         }
         if (!ready) { tables_wait<LUTS>(smem); ready = true; }
@@ -775,7 +775,7 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
     for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         EnvIn<N> in;
         load_state<WORDS>(states, b, in.lo, in.hi);
-        decode_state<N, WORDS>(sp, in.lo, in.hi, in.cell);
+        decode_state<N, WORDS, LUTS>(sp, in.lo, in.hi, in.cell);
         for (i64 t = 0; t < T; ++t) {
             const i64 o = t * (i64)B + b;
             const u64 env = env0 + (u64)b, stp = step0 + (u64)t;
