@@ -47,6 +47,12 @@ def lib():
         L.oracle_step.argtypes = [C.c_void_p, C.c_int64, u64p, u64p, i64p, f64p, u64p, u64p, f64p, f64p, u8p, u8p,
                                   u8p]
         L.oracle_step_mt.argtypes = L.oracle_step.argtypes + [C.c_int]
+        L.oracle_backup.argtypes = [C.c_void_p, C.c_int64, u64p, u64p, i64p, f64p, C.c_double, f64p]
+        L.oracle_backup_mt.argtypes = L.oracle_backup.argtypes + [C.c_int]
+        L.oracle_count_predecessors.restype = C.c_int64
+        L.oracle_count_predecessors.argtypes = [C.c_void_p, C.c_int64, u64p, u64p, i64p]
+        L.oracle_predecessors.argtypes = [C.c_void_p, C.c_int64, u64p, u64p, i64p, u64p, u64p]
+        L.oracle_project_states.argtypes = [C.c_void_p, C.c_int64, u64p, u64p, C.c_int, i32p, u64p, u64p]
         _lib = L
     return _lib
 
@@ -133,3 +139,38 @@ class COracle:
         else:
             lib().oracle_step(*args)
         return out
+
+    # ---- rows built after the hot path
+    def backup(self, s_lo, s_hi, action, V, gamma, threads=1):
+        """Q[b] = sum over P[s_b][a_b] of p * (r + gamma * V[s2]) in the row's order (states must fit one word)."""
+        s_lo = np.ascontiguousarray(s_lo, np.uint64)
+        s_hi = np.ascontiguousarray(s_hi, np.uint64)
+        action = np.ascontiguousarray(action, np.int64)
+        V = np.ascontiguousarray(V, np.float64)
+        Q = np.zeros(len(s_lo), np.float64)
+        if threads > 1:
+            lib().oracle_backup_mt(self._h, len(s_lo), s_lo, s_hi, action, V, float(gamma), Q, threads)
+        else:
+            lib().oracle_backup(self._h, len(s_lo), s_lo, s_hi, action, V, float(gamma), Q)
+        return Q
+
+    def predecessors(self, s_lo, s_hi):
+        """CSR of env.predecessors(s) for every state, each row sorted ascending."""
+        s_lo = np.ascontiguousarray(s_lo, np.uint64)
+        s_hi = np.ascontiguousarray(s_hi, np.uint64)
+        B = len(s_lo)
+        row_len = np.zeros(B, np.int64)
+        total = lib().oracle_count_predecessors(self._h, B, s_lo, s_hi, row_len)
+        row_ptr = np.zeros(B + 1, np.int64)
+        np.cumsum(row_len, out=row_ptr[1:])
+        p_lo, p_hi = np.zeros(total, np.uint64), np.zeros(total, np.uint64)
+        lib().oracle_predecessors(self._h, B, s_lo, s_hi, row_ptr, p_lo, p_hi)
+        return dict(row_ptr=row_ptr, pred_lo=p_lo, pred_hi=p_hi)
+
+    def project(self, s_lo, s_hi, agents):
+        s_lo = np.ascontiguousarray(s_lo, np.uint64)
+        s_hi = np.ascontiguousarray(s_hi, np.uint64)
+        agents = np.ascontiguousarray(agents, np.int32)
+        o_lo, o_hi = np.zeros(len(s_lo), np.uint64), np.zeros(len(s_lo), np.uint64)
+        lib().oracle_project_states(self._h, len(s_lo), s_lo, s_hi, len(agents), agents, o_lo, o_hi)
+        return o_lo, o_hi

@@ -324,6 +324,112 @@ void oracle_step(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uin
     }
 }
 
+/* ---- rows built after the hot path ------------------------------------------------------------ */
+
+/* The consumer loop of a planner over the table (the classic gym value-iteration backup that gym-mapf's downstream
+ * planners run on env.P, mapf_env.py:448-479):
+ *     q = sum([p * (r + gamma * V[s2]) for ((p, collision), s2, r, done) in env.P[s][a]])
+ * Python's sum() adds left to right starting from the int 0; every operation is one IEEE binary64 operation. */
+static double backup_row(const oracle_env *e, u128 s, int64_t a, const double *V, double gamma, uint64_t *t_lo,
+                         uint64_t *t_hi, double *t_p, double *t_r, uint8_t *t_d, uint8_t *t_c) {
+    int64_t len = emit_row(e, s, a, 0, t_lo, t_hi, t_p, t_r, t_d, t_c, NULL);
+    double q = 0.0;
+    for (int64_t j = 0; j < len; ++j) {
+        double gv = gamma * V[t_lo[j]];
+        double inner = t_r[j] + gv;
+        double term = t_p[j] * inner;
+        q = q + term;
+    }
+    return q;
+}
+
+static int64_t max_row(const oracle_env *e) {
+    int64_t m = 1;
+    for (int i = 0; i < e->n; ++i) m *= 3;
+    return m;
+}
+
+void oracle_backup(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uint64_t *s_hi, const int64_t *action,
+                   const double *V, double gamma, double *Q) {
+    int64_t m = max_row(e);
+    uint64_t *t_lo = malloc(m * 8), *t_hi = malloc(m * 8);
+    double *t_p = malloc(m * 8), *t_r = malloc(m * 8);
+    uint8_t *t_d = malloc(m), *t_c = malloc(m);
+    for (int64_t b = 0; b < B; ++b)
+        Q[b] = backup_row(e, ((u128)s_hi[b] << 64) | s_lo[b], action[b], V, gamma, t_lo, t_hi, t_p, t_r, t_d, t_c);
+    free(t_lo); free(t_hi); free(t_p); free(t_r); free(t_d); free(t_c);
+}
+
+/* mapf_env.py:414-425 -- the cells `_single_location_predecessors` returns for one cell: the results of moving
+ * DOWN, UP, LEFT, RIGHT, STAY from it (in that order), with duplicates kept out (the caller builds a set). */
+static int pred_cells(const oracle_env *e, int32_t cell, int32_t *out) {
+    static const int order[5] = {DOWN, UP, LEFT, RIGHT, STAY};
+    int r = e->rc_of[cell] / e->W, c = e->rc_of[cell] % e->W, k = 0;
+    for (int j = 0; j < 5; ++j) {
+        int32_t id = e->cell_of[shift_cell(e, r, c, order[j])];
+        int seen = 0;
+        for (int q = 0; q < k; ++q) seen |= out[q] == id;
+        if (!seen) out[k++] = id;
+    }
+    return k;
+}
+
+/* mapf_env.py:373-376, 426-434 -- |predecessors(s)| for B states */
+int64_t oracle_count_predecessors(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uint64_t *s_hi,
+                                  int64_t *row_len) {
+    int64_t total = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        int32_t ids[MAX_AGENTS], tmp[5];
+        decode_state(e, ((u128)s_hi[b] << 64) | s_lo[b], ids);
+        int64_t len = 1;
+        for (int i = 0; i < e->n; ++i) len *= pred_cells(e, ids[i], tmp);
+        row_len[b] = len;
+        total += len;
+    }
+    return total;
+}
+
+static int cmp_u128(const void *a, const void *b) {
+    u128 x = *(const u128 *)a, y = *(const u128 *)b;
+    return x < y ? -1 : x > y;
+}
+
+/* The predecessor sets as CSR, each row sorted ascending (the reference returns an unordered Python set). */
+void oracle_predecessors(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uint64_t *s_hi,
+                         const int64_t *row_ptr, uint64_t *p_lo, uint64_t *p_hi) {
+    for (int64_t b = 0; b < B; ++b) {
+        int32_t ids[MAX_AGENTS], opt[MAX_AGENTS][5], pick[MAX_AGENTS];
+        int k[MAX_AGENTS], digit[MAX_AGENTS];
+        decode_state(e, ((u128)s_hi[b] << 64) | s_lo[b], ids);
+        for (int i = 0; i < e->n; ++i) { k[i] = pred_cells(e, ids[i], opt[i]); digit[i] = 0; }
+        int64_t len = row_ptr[b + 1] - row_ptr[b], at = 0;
+        u128 *buf = malloc(len * sizeof(u128));
+        for (;;) {
+            for (int i = 0; i < e->n; ++i) pick[i] = opt[i][digit[i]];
+            buf[at++] = encode_state(e, pick);
+            int i = e->n - 1;
+            while (i >= 0 && ++digit[i] == k[i]) { digit[i] = 0; --i; }
+            if (i < 0) break;
+        }
+        qsort(buf, len, sizeof(u128), cmp_u128);
+        for (int64_t j = 0; j < len; ++j) { p_lo[row_ptr[b] + j] = (uint64_t)buf[j]; p_hi[row_ptr[b] + j] = (uint64_t)(buf[j] >> 64); }
+        free(buf);
+    }
+}
+
+/* utils.py:138-157 -- a joint state as the sub-env of `agents` (get_local_view) numbers it: the chosen agents'
+ * cells, in the sub-env's agent order, re-encoded with the same radix L. */
+void oracle_project_states(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uint64_t *s_hi, int n_sub,
+                           const int32_t *agents, uint64_t *o_lo, uint64_t *o_hi) {
+    for (int64_t b = 0; b < B; ++b) {
+        int32_t ids[MAX_AGENTS];
+        decode_state(e, ((u128)s_hi[b] << 64) | s_lo[b], ids);
+        u128 x = 0, w = 1;
+        for (int j = 0; j < n_sub; ++j) { x += (u128)ids[agents[j]] * w; w *= (u128)e->L; }
+        o_lo[b] = (uint64_t)x; o_hi[b] = (uint64_t)(x >> 64);
+    }
+}
+
 /* ---- multi-threaded drivers, used only as the timed CPU baseline (bench.py) -------------------------------- */
 typedef struct {
     const oracle_env *e; int64_t b0, b1;
@@ -377,4 +483,28 @@ void oracle_expand_mt(const oracle_env *e, int64_t B, const uint64_t *s_lo, cons
     }
     for (int t = 0; t < threads; ++t) pthread_join(tid[t], NULL);
     free(tid); free(jobs);
+}
+
+typedef struct {
+    const oracle_env *e; int64_t b0, b1;
+    const uint64_t *s_lo, *s_hi; const int64_t *action; const double *V; double gamma; double *Q;
+} backup_job;
+
+static void *backup_worker(void *arg) {
+    backup_job *j = arg;
+    oracle_backup(j->e, j->b1 - j->b0, j->s_lo + j->b0, j->s_hi + j->b0, j->action + j->b0, j->V, j->gamma, j->Q + j->b0);
+    return NULL;
+}
+
+void oracle_backup_mt(const oracle_env *e, int64_t B, const uint64_t *s_lo, const uint64_t *s_hi, const int64_t *action,
+                      const double *V, double gamma, double *Q, int threads) {
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    backup_job jobs[256];
+    for (int t = 0; t < threads; ++t) {
+        jobs[t] = (backup_job){e, B * t / threads, B * (t + 1) / threads, s_lo, s_hi, action, V, gamma, Q};
+        pthread_create(&th[t], NULL, backup_worker, &jobs[t]);
+    }
+    for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
 }

@@ -192,6 +192,19 @@ class OracleSpec:
         return {from_digits(combo, self.L) for combo in product(*per_agent)}
 
 
+    # -- the consumer loop of a planner over P (gym value-iteration backup on `mapf_env.py:448-479`'s rows)
+    def backup(self, s, a, V, gamma):
+        acc = 0  # explicit left-to-right adds: the builtin sum() of floats is compensated since Python 3.12
+        for (p, _c, s2, r, _d) in self.row(s, a):
+            acc = acc + p * (r + gamma * V[s2])
+        return acc
+
+    # -- `utils.py:138-157`: the state as the sub-env of `agents` numbers it
+    def project(self, s, agents):
+        ids = to_digits(s, self.L, self.n)
+        return from_digits([ids[i] for i in agents], self.L)
+
+
 def spec_from_reference_env(env, soc):
     """Build an OracleSpec from a live reference `MapfEnv` (golden generation only)."""
     h = len(env.grid)

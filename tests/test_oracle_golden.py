@@ -143,3 +143,51 @@ def test_fp_constants_known_answers():
     assert p.hex() == "0x1.999999999999ap-1" and rf.hex() == "0x1.999999999999ap-4"
     assert (p + rf).hex() == "0x1.ccccccccccccdp-1" and (p + rf) + rf == 1.0
     assert (p * p).hex() == "0x1.47ae147ae147cp-1"
+
+
+# ---- rows built after the hot path: the oracle against reference-generated fixtures -------------
+@pytest.mark.parametrize("name", G.names("backup_"))
+def test_oracle_backup(name):
+    spec, d = G.load(name)
+    ora = c_env(spec)
+    V = G.bits_to_f64(d["v_bits"])
+    gamma = float(G.bits_to_f64(np.array([d["gamma_bits"]]))[0])
+    q = ora.backup(d["state_lo"], d["state_hi"], d["action"], V, gamma)
+    assert np.array_equal(G.f64_to_bits(q), d["q_bits"])
+    # the pure-Python restatement on a sample
+    py = py_env(spec)
+    for i in range(0, len(d["action"]), max(1, len(d["action"]) // 150)):
+        got = py.backup(int(d["state_lo"][i]), int(d["action"][i]), V.tolist(), gamma)
+        assert G.py_bits(got) == int(d["q_bits"][i])
+
+
+@pytest.mark.parametrize("name", G.names("preds_"))
+def test_oracle_predecessors(name):
+    spec, d = G.load(name)
+    ora = c_env(spec)
+    got = ora.predecessors(d["state_lo"], d["state_hi"])
+    assert np.array_equal(got["row_ptr"], d["row_ptr"])
+    assert np.array_equal(got["pred_lo"], d["pred_lo"]) and np.array_equal(got["pred_hi"], d["pred_hi"])
+    py = py_env(spec)
+    for i in range(0, len(d["state_lo"]), max(1, len(d["state_lo"]) // 5)):
+        if d["row_ptr"][i + 1] - d["row_ptr"][i] > 50000:
+            continue
+        want = sorted(G.big(lo, hi) for lo, hi in zip(d["pred_lo"][d["row_ptr"][i]:d["row_ptr"][i + 1]],
+                                                      d["pred_hi"][d["row_ptr"][i]:d["row_ptr"][i + 1]]))
+        assert sorted(py.predecessors(G.big(d["state_lo"][i], d["state_hi"][i]))) == want
+
+
+@pytest.mark.parametrize("name", G.names("project_"))
+def test_oracle_projection(name):
+    spec, d = G.load(name)
+    ora = c_env(spec)
+    py = py_env(spec)
+    k = 0
+    while "agents_%d" % k in d:
+        agents = d["agents_%d" % k]
+        lo, hi = ora.project(d["state_lo"], d["state_hi"], agents)
+        assert np.array_equal(lo, d["proj_lo_%d" % k]) and np.array_equal(hi, d["proj_hi_%d" % k])
+        assert py.project(G.big(d["state_lo"][3], d["state_hi"][3]), [int(a) for a in agents]) == \
+            G.big(d["proj_lo_%d" % k][3], d["proj_hi_%d" % k][3])
+        k += 1
+    assert k >= 5
