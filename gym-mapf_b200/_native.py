@@ -19,7 +19,8 @@ FLAG_DONE, FLAG_COLLISION = 1, 2
 EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
            "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_rollout", "mapf_step_host",
-           "mapf_last_error", "mapf_version"]
+           "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_count_predecessors", "mapf_predecessors",
+           "mapf_projected_words", "mapf_project_states", "mapf_last_error", "mapf_version"]
 
 
 class MapfSpec(C.Structure):
@@ -86,6 +87,13 @@ def lib():
         L.mapf_step.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
         L.mapf_rollout.argtypes = [vp, vp, vp, i64, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
         L.mapf_step_host.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp]
+        L.mapf_backup.argtypes = [vp, vp, vp, i64, vp, i64, C.c_double, vp, vp]
+        L.mapf_backup_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, i64, C.c_double, vp, vp]
+        L.mapf_greedy.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mapf_count_predecessors.argtypes = [vp, vp, i64, vp, vp]
+        L.mapf_predecessors.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mapf_projected_words.argtypes = [vp, i32]
+        L.mapf_project_states.argtypes = [vp, vp, i64, vp, i32, vp, vp]
         L.mapf_last_error.restype = C.c_char_p
         L.mapf_version.restype = C.c_char_p
         _lib = L
@@ -296,4 +304,55 @@ class Engine:
         check(lib().mapf_step_host(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
                                    OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
                                    _ptr(coll)))
+        return out
+
+    # ---- rows next to the hot path ----------------------------------------------------------
+    def backup(self, states, actions, V, gamma, out=None):
+        """Q[b] = sum over P[states[b]][actions[b]], in order, of p * (r + gamma * V[s2]) -- no table is written."""
+        import torch
+        B = states.shape[0]
+        Q = out if out is not None else torch.empty(B, dtype=torch.float64, device=self.torch_device)
+        check(lib().mapf_backup(self._h, _ptr(states), _ptr(actions), B, _ptr(V), V.shape[0], float(gamma), _ptr(Q),
+                                self._stream()))
+        return Q
+
+    def backup_range(self, s_begin, n_states, V, gamma, out=None):
+        """The same for the slab [s_begin, s_begin + n_states) x all actions: Q[n_states, nA]."""
+        import torch
+        sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
+        Q = out if out is not None else torch.empty((n_states, self.nA), dtype=torch.float64, device=self.torch_device)
+        check(lib().mapf_backup_range(self._h, C.byref(sb), n_states, _ptr(V), V.shape[0], float(gamma), _ptr(Q),
+                                      self._stream()))
+        return Q
+
+    def greedy(self, Q):
+        """(max over actions, first argmax) of a Q[n_states, nA] slab."""
+        import torch
+        n_states = Q.shape[0]
+        V = torch.empty(n_states, dtype=torch.float64, device=self.torch_device)
+        pi = torch.empty(n_states, dtype=torch.int32, device=self.torch_device)
+        check(lib().mapf_greedy(self._h, _ptr(Q), n_states, _ptr(V), _ptr(pi), self._stream()))
+        return V, pi
+
+    def predecessors(self, states):
+        """CSR (row_ptr, pred_states) of MapfEnv.predecessors for every state."""
+        import torch
+        B = states.shape[0]
+        row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_count_predecessors(self._h, _ptr(states), B, _ptr(row_len), self._stream()))
+        row_ptr = self._scan(row_len)
+        pred = self.new_states(int(row_ptr[-1].item()))
+        check(lib().mapf_predecessors(self._h, _ptr(states), B, _ptr(row_ptr), _ptr(pred), self._stream()))
+        return row_ptr, pred
+
+    def project(self, states, agents):
+        """The states as the sub-env of `agents` (get_local_view) numbers them: int64[B] or int64[B, 2]."""
+        import torch
+        B = states.shape[0]
+        agents = np.ascontiguousarray(agents, dtype=np.int32)
+        words = lib().mapf_projected_words(self._h, len(agents))
+        if words < 0:
+            check(words)
+        out = torch.empty((B,) if words == 1 else (B, 2), dtype=torch.int64, device=self.torch_device)
+        check(lib().mapf_project_states(self._h, _ptr(states), B, _ptr(agents), len(agents), _ptr(out), self._stream()))
         return out

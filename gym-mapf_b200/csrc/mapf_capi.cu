@@ -62,7 +62,7 @@ struct mapf_ctx {
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
     int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout_tape = 0;
-    int grid_expand = 0, grid_expand_range = 0, grid_plain = 0;
+    int grid_expand = 0, grid_expand_range = 0, grid_plain = 0, grid_backup = 0, grid_backup_range = 0;
     KernelSet ks;
     u32 pat_triple[MAPF_MAX_PATTERNS];  // merge patterns (see PatternList)
     int n_patterns = 0;
@@ -452,8 +452,11 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand},
-        {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range}};
+        {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range},
+        {ctx->ks.backup, ctx->smem_expand, &ctx->grid_backup},
+        {ctx->ks.backup_range, ctx->smem_expand, &ctx->grid_backup_range}};
     for (auto &pl : plan) {
+        if (!pl.fn) continue;  // two-word states have no backup kernels
         if (pl.smem > 48 * 1024)
             CTX_TRY(cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         int rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
@@ -645,6 +648,103 @@ extern "C" int mapf_checksum(const mapf_ctx *ctx, int64_t n_records, int64_t ind
     k_checksum<<<grid_for(n_records, 256, ctx->grid_plain), 256, 0, (cudaStream_t)stream>>>(
         ctx->sp.words, n_records, index_base, (const u64 *)next_state, prob, reward, flags, (u64 *)out8);
     CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rows next to the hot path: Bellman backup, predecessors, local-view projection
+// ---------------------------------------------------------------------------------------------------------------
+static int backup_impl(const mapf_ctx *ctx, bool range, const void *states, const int32_t *actions, u64 sb_lo, int64_t B,
+                       const double *V, int64_t v_len, double gamma, double *Q, void *stream) {
+    if (ctx->sp.words != 1)
+        return fail(MAPF_ERR_UNSUPPORTED, "backup: a value vector over L**n = %d**%d states cannot exist", ctx->sp.L, ctx->sp.n);
+    if (!V || !Q || v_len < 0 || (u64)v_len <= ctx->sp.smax[0])
+        return fail(MAPF_ERR_INVALID, "backup: V must hold nS = %llu values (v_len = %lld)",
+                    (unsigned long long)ctx->sp.smax[0] + 1, (long long)v_len);
+    if (B == 0) return MAPF_OK;
+    DeviceGuard g(ctx->device);
+    DevSpec sp = ctx->sp;
+    void *args[] = {&sp, &states, &actions, &sb_lo, &B, &V, &gamma, &Q};
+    const int grid = grid_for(B, ctx->threads, range ? ctx->grid_backup_range : ctx->grid_backup);
+    LAUNCH(range ? ctx->ks.backup_range : ctx->ks.backup, grid, ctx->threads, ctx->smem_expand, stream, args);
+    return MAPF_OK;
+}
+
+extern "C" int mapf_backup(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, const double *V,
+                           int64_t v_len, double gamma, double *Q, void *stream) {
+    if (!ctx || B < 0 || (B > 0 && (!states || !actions))) return fail(MAPF_ERR_INVALID, "mapf_backup: bad argument");
+    return backup_impl(ctx, false, states, actions, 0, B, V, v_len, gamma, Q, stream);
+}
+
+extern "C" int mapf_backup_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_states, const double *V,
+                                 int64_t v_len, double gamma, double *Q, void *stream) {
+    if (!ctx || !s_begin) return fail(MAPF_ERR_INVALID, "mapf_backup_range: bad argument");
+    int64_t B = 0;
+    int rc = range_rows(ctx, n_states, &B);
+    if (rc) return rc;
+    if (s_begin[1] != 0 || (n_states > 0 && s_begin[0] + (u64)n_states - 1 > ctx->sp.smax[0]))
+        return fail(MAPF_ERR_INVALID, "mapf_backup_range: the slab leaves the state space");
+    return backup_impl(ctx, true, nullptr, nullptr, s_begin[0], B, V, v_len, gamma, Q, stream);
+}
+
+extern "C" int mapf_greedy(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy,
+                           void *stream) {
+    if (!ctx || n_states < 0 || (n_states > 0 && !Q)) return fail(MAPF_ERR_INVALID, "mapf_greedy: bad argument");
+    if (n_states == 0) return MAPF_OK;
+    DeviceGuard g(ctx->device);
+    const int64_t nA = (int64_t)ctx->sp.nA;
+    k_greedy<<<grid_for(n_states * 32, 256, ctx->grid_plain), 256, 0, (cudaStream_t)stream>>>(Q, n_states, nA, V_out, policy);
+    CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
+
+extern "C" int mapf_count_predecessors(const mapf_ctx *ctx, const void *states, int64_t B, int64_t *row_len, void *stream) {
+    if (!ctx || B < 0 || (B > 0 && (!states || !row_len))) return fail(MAPF_ERR_INVALID, "mapf_count_predecessors: bad argument");
+    if (B == 0) return MAPF_OK;
+    DeviceGuard g(ctx->device);
+    DevSpec sp = ctx->sp;
+    void *args[] = {&sp, &states, &B, &row_len};
+    LAUNCH(ctx->ks.pred_count, grid_for(B, 256, ctx->grid_plain), 256, 0, stream, args);
+    return MAPF_OK;
+}
+
+extern "C" int mapf_predecessors(const mapf_ctx *ctx, const void *states, int64_t B, const int64_t *row_ptr, void *pred,
+                                 void *stream) {
+    if (!ctx || B < 0 || (B > 0 && (!states || !row_ptr || !pred))) return fail(MAPF_ERR_INVALID, "mapf_predecessors: bad argument");
+    if (B == 0) return MAPF_OK;
+    DeviceGuard g(ctx->device);
+    DevSpec sp = ctx->sp;
+    void *args[] = {&sp, &states, &B, &row_ptr, &pred};
+    LAUNCH(ctx->ks.pred_emit, grid_for(B * 32, 256, ctx->grid_plain), 256, 0, stream, args);
+    return MAPF_OK;
+}
+
+extern "C" int mapf_projected_words(const mapf_ctx *ctx, int32_t n_sub) {
+    if (!ctx || n_sub < 1 || n_sub > ctx->sp.n) return fail(MAPF_ERR_INVALID, "mapf_projected_words: bad argument");
+    u128 v = 1;
+    for (int i = 0; i < n_sub; ++i) v *= (u128)ctx->sp.L;
+    return v < ((u128)1 << 63) ? 1 : 2;
+}
+
+extern "C" int mapf_project_states(const mapf_ctx *ctx, const void *states, int64_t B, const int32_t *agents, int32_t n_sub,
+                                   void *out_states, void *stream) {
+    if (!ctx || B < 0 || !agents || n_sub < 1 || n_sub > ctx->sp.n || (B > 0 && (!states || !out_states)))
+        return fail(MAPF_ERR_INVALID, "mapf_project_states: bad argument");
+    AgentList sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.n = n_sub;
+    for (int j = 0; j < n_sub; ++j) {
+        if (agents[j] < 0 || agents[j] >= ctx->sp.n) return fail(MAPF_ERR_INVALID, "agent index %d out of range", agents[j]);
+        for (int q = 0; q < j; ++q)
+            if (agents[q] == agents[j]) return fail(MAPF_ERR_INVALID, "agent index %d listed twice", agents[j]);
+        sub.idx[j] = agents[j];
+    }
+    sub.words_out = mapf_projected_words(ctx, n_sub);
+    if (B == 0) return MAPF_OK;
+    DeviceGuard g(ctx->device);
+    DevSpec sp = ctx->sp;
+    void *args[] = {&sp, &states, &B, &sub, &out_states};
+    LAUNCH(ctx->ks.project, grid_for(B, 256, ctx->grid_plain), 256, 0, stream, args);
     return MAPF_OK;
 }
 

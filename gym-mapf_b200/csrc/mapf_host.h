@@ -11,6 +11,8 @@ struct KernelSet {
     const void *expand = nullptr, *expand_range = nullptr;
     const void *count = nullptr, *count_range = nullptr;
     const void *decode = nullptr, *encode = nullptr;
+    const void *backup = nullptr, *backup_range = nullptr;  // k_backup<N, LUTS, RANGE>; one-word states only
+    const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;
     size_t expand_slab_bytes = 0;        // per warp
 };
 

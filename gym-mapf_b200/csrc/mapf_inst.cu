@@ -20,6 +20,13 @@ static void fill(KernelSet *k) {
     k->count_range = (const void *)k_count<N, W, true>;
     k->decode = (const void *)k_decode<N, W>;
     k->encode = (const void *)k_encode<N, W>;
+    if (W == 1) {
+        k->backup = (const void *)k_backup<N, LUTS, false>;
+        k->backup_range = (const void *)k_backup<N, LUTS, true>;
+    }
+    k->pred_count = (const void *)k_pred_count<N, W>;
+    k->pred_emit = (const void *)k_pred_emit<N, W>;
+    k->project = (const void *)k_project<N, W>;
     k->expand_slab_bytes = sizeof(ExpandSlab<N>);
 }
 

@@ -383,6 +383,105 @@ __device__ __forceinline__ u32 list_conflict_pairs(const int (&cell)[N], const u
     return count;
 }
 
+// Phase A for one row (lane = row): decode (s, a), terminal test, the N move-table entries, the row length and its
+// reciprocal, the conflict pre-filter; everything phase B needs goes to column `lane` of the warp's slab.
+// Returns the row length.
+template <int N, int WORDS, bool LUTS, bool RANGE>
+__device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTables &tb, ExpandSlab<N> &sl, int lane,
+                                                const u64 *__restrict__ states, const int *__restrict__ actions,
+                                                u64 sb_lo, u64 sb_hi, i64 b) {
+    u64 slo, shi;
+    u32 a;
+    row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, slo, shi, a);
+    int cell[N], act[N];
+    u64 ent[N];
+    decode_state<N, WORDS, LUTS>(sp, slo, shi, cell);
+    decode_action<N>(a, act);
+    const bool term = is_terminal<N>(sp, cell, slo, shi);
+    u32 len = 1, twos = 0, threes = 0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
+        ent[i] = ENT_CORE(ent[i]);  // phase B reads k as e >> 56
+        sl.ent[i][lane] = ent[i];
+        sl.prev[i][lane] = (u16)cell[i];
+        const u32 k = ENT_K(ent[i]);
+        len *= k;
+        twos += k == 2u ? 1u : 0u;
+        threes += k == 3u ? 1u : 0u;
+    }
+    if (term) len = 1;
+    sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
+    sl.st[0][lane] = slo;
+    sl.st[1][lane] = shi;
+    sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
+    // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
+    // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
+    u32 n_pairs = 0;
+    if (!term) {
+        if (N >= EXPAND_LIST_MIN_AGENTS) n_pairs = list_conflict_pairs<N>(cell, ent, sl.pair, lane);
+        else n_pairs = any_pair_can_conflict<N>(cell, ent) ? EXPAND_MAX_PAIRS + 1u : 0u;
+    }
+    sl.flag[lane] = (u8)((term ? 1u : 0u) | (n_pairs <= EXPAND_MAX_PAIRS ? n_pairs << 1 : 16u));
+    return len;
+}
+
+// One record of P[s][a] (mapf_env.py:448-479): `o` is its index within row `row` of the warp's slab.
+struct RecordOut {
+    u64 lo, hi;      // next state
+    double p, reward;
+    u32 flags;       // MAPF_FLAG_DONE | MAPF_FLAG_COLLISION
+};
+
+template <int N, int WORDS>
+__device__ __forceinline__ RecordOut expand_record(const DevSpec &sp, const SmemTables &tb, const ExpandSlab<N> &sl,
+                                                   int row, u32 flag, u32 o) {
+    RecordOut out;  // the caller has dealt with terminal rows (flag bit 0)
+    // Outcome digits: itertools.product, agent 0 slowest (mapf_env.py:467).  With T = row length and o the
+    // record's index in the row, x = (o + 1/2) / T as a 32-bit fraction; multiplying by k_0 leaves digit 0 in
+    // the integer part and the fraction of the remaining digits, and so on: ONE wide multiply per agent.
+    // (T <= 3**13 < 2**21: the 2**-32 truncation of x grows to at most 2**-11 of a digit, the half-unit
+    // offset keeps every digit 2**-22 away from an integer boundary.)
+    u32 x = (u32)(((u64)(2u * o + 1u) * sl.rcp[row]) >> 32);
+    int nxt[N];
+    u32 pj[N], dv = 0;  // dv: the digits, two bits per agent
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const u64 e = sl.ent[i][row];
+        const u64 wide = (u64)x * (u64)((u32)(e >> 56));  // bits 58..63 of a slab entry are zero: this is k
+        const u32 d = (u32)(wide >> 32);
+        x = (u32)wide;
+        nxt[i] = (int)ent_dest(e, d);
+        pj[i] = ENT_POFF(e) + d * 8u;
+        if (N >= EXPAND_LIST_MIN_AGENTS) dv += d << (2 * i);
+    }
+    // probability: left-to-right product (mapf_env.py:468)
+    double p = lds_f64<MAPF_SMEM_PP>(tb.base + pj[0]);
+#pragma unroll
+    for (int i = 1; i < N; ++i) p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + pj[i]));
+    // reward / done / collision (mapf_env.py:225-235): clash beats goal
+    bool clash = false;
+    if (flag & 16u) {
+        int prv[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) prv[i] = (int)sl.prev[i][row];
+        clash = has_clash<N>(prv, nxt);
+    } else if (N >= EXPAND_LIST_MIN_AGENTS) {
+        for (u32 q = 0; q < (flag >> 1); ++q) {
+            const u32 desc = sl.pair[q][row];
+            const u32 di = (dv >> (desc & 31u)) & 3u, dj = (dv >> ((desc >> 5) & 31u)) & 3u;
+            clash = clash || ((desc >> (10u + 3u * di + dj)) & 1u);
+        }
+    }
+    encode_state<N, WORDS>(sp, nxt, out.lo, out.hi);
+    const bool goal = out.lo == sp.sgoal[0] && out.hi == sp.sgoal[1];  // every agent on its goal
+    const int kind = clash ? 1 : (goal ? 2 : 0);
+    out.p = p;
+    out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[row]) * 8u);
+    out.flags = (kind != 0 ? 1u : 0u) | (clash ? 2u : 0u);
+    return out;
+}
+
 template <int N, int WORDS, bool LUTS, bool RANGE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
 k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
@@ -422,41 +521,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
         const i64 start = b < B ? row_ptr[b] : M;
         const i64 batch_begin = __shfl_sync(FULL, start, 0);
         const bool need = b < B && start < hi;
-        u32 len = 0;
-        if (need) {
-            u64 slo, shi;
-            u32 a;
-            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, slo, shi, a);
-            int cell[N], act[N];
-            u64 ent[N];
-            decode_state<N, WORDS, LUTS>(sp, slo, shi, cell);
-            decode_action<N>(a, act);
-            const bool term = is_terminal<N>(sp, cell, slo, shi);
-            len = 1;
-            u32 twos = 0, threes = 0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
-                ent[i] = ENT_CORE(ent[i]);  // phase B reads k as e >> 56
-                sl.ent[i][lane] = ent[i];
-                sl.prev[i][lane] = (u16)cell[i];
-                const u32 k = ENT_K(ent[i]);
-                len *= k;
-                twos += k == 2u ? 1u : 0u;
-                threes += k == 3u ? 1u : 0u;
-            }
-            if (term) len = 1;
-            sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
-            sl.st[0][lane] = slo;
-            sl.st[1][lane] = shi;
-            sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
-            // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
-            // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
-            u32 n_pairs;
-            if (N >= EXPAND_LIST_MIN_AGENTS) n_pairs = term ? 0u : list_conflict_pairs<N>(cell, ent, sl.pair, lane);
-            else n_pairs = any_pair_can_conflict<N>(cell, ent) ? EXPAND_MAX_PAIRS + 1u : 0u;
-            sl.flag[lane] = (u8)((term ? 1u : 0u) | (n_pairs <= EXPAND_MAX_PAIRS ? n_pairs << 1 : 16u));
-        }
+        const u32 len = need ? expand_row_setup<N, WORDS, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, sb_hi, b) : 0u;
         u32 incl = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -491,55 +556,222 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
                 flags[idx] = 1;
                 continue;
             }
-            // Outcome digits: itertools.product, agent 0 slowest (mapf_env.py:467).  With T = row length and o the
-            // record's index in the row, x = (o + 1/2) / T as a 32-bit fraction; multiplying by k_0 leaves digit 0 in
-            // the integer part and the fraction of the remaining digits, and so on: ONE wide multiply per agent.
-            // (T <= 3**13 < 2**21: the 2**-32 truncation of x grows to at most 2**-11 of a digit, the half-unit
-            // offset keeps every digit 2**-22 away from an integer boundary.)
-            const u32 o = (u32)rel - sl.pref[row];
-            u32 x = (u32)(((u64)(2u * o + 1u) * sl.rcp[row]) >> 32);
-            int nxt[N];
-            u32 pj[N], dv = 0;  // dv: the digits, two bits per agent
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const u64 e = sl.ent[i][row];
-                const u64 wide = (u64)x * (u64)((u32)(e >> 56));  // bits 58..63 of an entry are zero: this is k
-                const u32 d = (u32)(wide >> 32);
-                x = (u32)wide;
-                nxt[i] = (int)ent_dest(e, d);
-                pj[i] = ENT_POFF(e) + d * 8u;
-                if (N >= EXPAND_LIST_MIN_AGENTS) dv += d << (2 * i);
-            }
-            // probability: left-to-right product (mapf_env.py:468)
-            double p = lds_f64<MAPF_SMEM_PP>(tb.base + pj[0]);
-#pragma unroll
-            for (int i = 1; i < N; ++i) p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + pj[i]));
-            // reward / done / collision (mapf_env.py:225-235): clash beats goal
-            bool clash = false;
-            if (flag & 16u) {
-                int prv[N];
-#pragma unroll
-                for (int i = 0; i < N; ++i) prv[i] = (int)sl.prev[i][row];
-                clash = has_clash<N>(prv, nxt);
-            } else if (N >= EXPAND_LIST_MIN_AGENTS) {
-                for (u32 q = 0; q < (flag >> 1); ++q) {
-                    const u32 desc = sl.pair[q][row];
-                    const u32 di = (dv >> (desc & 31u)) & 3u, dj = (dv >> ((desc >> 5) & 31u)) & 3u;
-                    clash = clash || ((desc >> (10u + 3u * di + dj)) & 1u);
-                }
-            }
-            u64 nlo, nhi;
-            encode_state<N, WORDS>(sp, nxt, nlo, nhi);
-            const bool goal = nlo == sp.sgoal[0] && nhi == sp.sgoal[1];  // every agent on its goal
-            const int kind = clash ? 1 : (goal ? 2 : 0);
-            store_state<WORDS>(next_state, idx, nlo, nhi);
-            prob[idx] = p;
-            reward[idx] = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[row]) * 8u);
-            flags[idx] = (u8)((kind != 0 ? 1 : 0) | (clash ? 2 : 0));
+            const RecordOut rec = expand_record<N, WORDS>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row]);
+            store_state<WORDS>(next_state, idx, rec.lo, rec.hi);
+            prob[idx] = rec.p;
+            reward[idx] = rec.reward;
+            flags[idx] = (u8)rec.flags;
         }
         if (batch_end >= hi || r + 32 >= B) break;
         r += 32;
         __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// Bellman backup over the table without materialising it
+// =====================================================================================================
+//   Q[b] = 0; for ((p, collision), s2, r, done) in P[s_b][a_b]:  Q[b] += p * (r + gamma * V[s2])
+// with every operation a single IEEE binary64 operation, in the row's order -- what a planner's loop over
+// env.P[s][a] computes.  Rows are taken 32 at a time by a warp (phase A as in k_expand); phase B evaluates the
+// records of those rows 32 at a time, one per lane (the expensive part: outcome digits, conflict test, encode, the
+// gather of V), and then adds the 32 terms IN ORDER: every lane walks the window's terms through shuffles, so the
+// sum of a row is associated exactly like the sequential loop; lane i keeps row i's result and the warp stores its
+// 32 results in one coalesced segment.  Nothing but Q is written: the 25 B/record of the table never exist.
+template <int N, bool LUTS, bool RANGE>
+__global__ void __launch_bounds__(MAPF_MAX_THREADS)
+k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, i64 B,
+         const double *__restrict__ V, double gamma, double *__restrict__ Q) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemTables tb = tables_begin<LUTS>(sp, smem);
+    const u32 FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const u32 lane_le = 0xffffffffu >> (31 - lane);
+    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
+    const i64 n_batches = (B + 31) >> 5;
+    const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
+    tables_wait<LUTS>(smem);
+    for (i64 batch = (i64)blockIdx.x * (blockDim.x >> 5) + wid; batch < n_batches; batch += n_warps) {
+        const i64 b = batch * 32 + lane;
+        const bool need = b < B;
+        const u32 len = need ? expand_row_setup<N, 1, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, 0ull, b) : 0u;
+        u32 incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = (int)__shfl_sync(FULL, incl, 31);
+        const int myrel = (int)(incl - len);
+        sl.pref[lane] = (u32)myrel;
+        __syncwarp();
+        double acc = 0.0, mine = 0.0;  // acc: running sum of the current row (identical in every lane)
+        int cur = 0, rows_before = 0;  // cur: the row acc belongs to
+        for (int wrel = 0; wrel < total; wrel += 32) {
+            const bool inwin = need && myrel >= wrel && myrel < wrel + 32;
+            const u32 heads = __reduce_or_sync(FULL, inwin ? 1u << (myrel - wrel) : 0u);
+            const int row = rows_before + __popc(heads & lane_le) - 1;
+            rows_before += __popc(heads);
+            const int rel = wrel + lane;
+            double term = 0.0;
+            if (rel < total) {
+                const u32 flag = sl.flag[row];
+                if (flag & 1u) {  // the single record of a terminal state: (1.0, s, 0, True)
+                    term = __dmul_rn(1.0, __dadd_rn(0.0, __dmul_rn(gamma, __ldg(V + sl.st[0][row]))));
+                } else {
+                    const RecordOut rec = expand_record<N, 1>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row]);
+                    term = __dmul_rn(rec.p, __dadd_rn(rec.reward, __dmul_rn(gamma, __ldg(V + rec.lo))));
+                }
+            }
+            const int cnt = total - wrel < 32 ? total - wrel : 32;
+            for (int j = 0; j < cnt; ++j) {  // the ordered sum; `heads` bit j: a new row starts at term j
+                const double tj = __shfl_sync(FULL, term, j);
+                if (((heads >> j) & 1u) && (wrel + j) != 0) {
+                    if (lane == cur) mine = acc;
+                    acc = 0.0;
+                    ++cur;
+                }
+                acc = __dadd_rn(acc, tj);
+            }
+        }
+        if (lane == cur) mine = acc;
+        if (need) Q[b] = mine;
+        __syncwarp();
+    }
+}
+
+// V[s] = max_a Q[s][a], policy[s] = the first a that attains it (np.argmax); one warp per state.
+static __global__ void __launch_bounds__(256)
+k_greedy(const double *__restrict__ Q, i64 n_states, i64 nA, double *__restrict__ V_out, int *__restrict__ policy) {
+    const int lane = threadIdx.x & 31;
+    const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
+    for (i64 s = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_states; s += warps) {
+        const double *q = Q + s * nA;
+        double best = 0.0;
+        i64 arg = -1;
+        for (i64 a = lane; a < nA; a += 32) {
+            const double v = q[a];
+            if (arg < 0 || v > best) { best = v; arg = a; }  // strictly greater: the first maximum stays
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const i64 oa = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+        }
+        if (lane == 0) {
+            if (V_out) V_out[s] = best;
+            if (policy) policy[s] = (int)arg;
+        }
+    }
+}
+
+// =====================================================================================================
+// predecessors(s) (mapf_env.py:373-376, 414-434)
+// =====================================================================================================
+// Per agent the candidate cells are where DOWN, UP, LEFT, RIGHT, STAY lead from its cell (the reference walks the
+// move backwards with the same clamp / obstacle rule), i.e. the intended destinations in the move table; equal
+// cells are kept once (the reference builds a set) and the joint set is their cartesian product, emitted with
+// agent 0 slowest.
+template <int N>
+__device__ __forceinline__ u32 pred_options(const DevSpec &sp, u32 cell, u32 (&out)[5]) {
+    const int order[5] = {3, 1, 4, 2, 0};  // DOWN, UP, LEFT, RIGHT, STAY (mapf_env.py:416-420)
+    u32 k = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const u32 id = (u32)__ldg(sp.lut + cell * 5u + order[j]) & 0xffffu;  // intended destination = slot 0
+        bool seen = false;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) seen = seen || (q < (int)k && out[q] == id);
+        if (!seen) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+                if (q == (int)k) out[q] = id;
+            ++k;
+        }
+    }
+    return k;
+}
+
+template <int N, int WORDS>
+__global__ void __launch_bounds__(256) k_pred_count(DevSpec sp, const u64 *__restrict__ states, i64 B, i64 *__restrict__ row_len) {
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        load_state<WORDS>(states, b, lo, hi);
+        int cell[N];
+        decode_state<N, WORDS>(sp, lo, hi, cell);
+        i64 len = 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            u32 opt[5];
+            len *= (i64)pred_options<N>(sp, (u32)cell[i], opt);
+        }
+        row_len[b] = len;
+    }
+}
+
+// one warp per state: the joint combinations are dealt to the lanes, record row_ptr[b] + j holds combination j
+template <int N, int WORDS>
+__global__ void __launch_bounds__(256)
+k_pred_emit(DevSpec sp, const u64 *__restrict__ states, i64 B, const i64 *__restrict__ row_ptr, u64 *__restrict__ pred) {
+    const int lane = threadIdx.x & 31;
+    const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
+    for (i64 b = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < B; b += warps) {
+        u64 lo, hi;
+        load_state<WORDS>(states, b, lo, hi);
+        int cell[N];
+        decode_state<N, WORDS>(sp, lo, hi, cell);
+        u32 opt[N][5], k[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) k[i] = pred_options<N>(sp, (u32)cell[i], opt[i]);
+        const i64 base = row_ptr[b], len = row_ptr[b + 1] - base;
+        for (i64 j = lane; j < len; j += 32) {
+            u64 o = (u64)j;
+            int pick[N];
+#pragma unroll
+            for (int i = N - 1; i >= 0; --i) {  // agent 0 slowest
+                const u32 d = (u32)(o % k[i]);
+                o /= k[i];
+                u32 c = opt[i][0];
+#pragma unroll
+                for (int q = 1; q < 5; ++q) c = d == (u32)q ? opt[i][q] : c;
+                pick[i] = (int)c;
+            }
+            u64 plo, phi;
+            encode_state<N, WORDS>(sp, pick, plo, phi);
+            store_state<WORDS>(pred, base + j, plo, phi);
+        }
+    }
+}
+
+// =====================================================================================================
+// A joint state as an agent subset sees it (get_local_view, utils.py:138-157)
+// =====================================================================================================
+struct AgentList {
+    int idx[16];
+    int n;
+    int words_out;
+};
+
+template <int N, int WORDS>
+__global__ void __launch_bounds__(256)
+k_project(DevSpec sp, const u64 *__restrict__ states, i64 B, AgentList sub, u64 *__restrict__ out) {
+    for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
+        u64 lo, hi;
+        load_state<WORDS>(states, b, lo, hi);
+        int cell[N];
+        decode_state<N, WORDS>(sp, lo, hi, cell);
+        // little-endian radix L over the chosen agents, in the sub-env's agent order (__init__.py:70-79)
+        unsigned __int128 x = 0, w = 1;
+        for (int j = 0; j < sub.n; ++j) {
+            int c = cell[0];
+#pragma unroll
+            for (int i = 1; i < N; ++i) c = sub.idx[j] == i ? cell[i] : c;
+            x += (unsigned __int128)(u32)c * w;
+            w *= (unsigned __int128)(u32)sp.L;
+        }
+        if (sub.words_out == 1) out[b] = (u64)x;
+        else { out[2 * b] = (u64)x; out[2 * b + 1] = (u64)(x >> 64); }
     }
 }
 

@@ -116,3 +116,48 @@ class VecMapfEnv:
         keys = ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi", "sum_prob_bits", "sum_reward_bits",
                 "ordered"]
         return dict(zip(keys, (int(x) for x in v)))
+
+    # ---- consumers of the table -----------------------------------------------------------------
+    def backup(self, V, gamma, states=None, actions=None, s_begin=0, n_states=None):
+        """Bellman backup without materialising the table: for explicit (states, actions) pairs a float64[B], else
+        Q[n_states, nA] of the slab [s_begin, s_begin + n_states) (default: every state).  Each entry is
+        `q = 0; for ((p, c), s2, r, done) in P[s][a]: q += p * (r + gamma * V[s2])`, bit for bit."""
+        if states is not None:
+            return self.engine.backup(states, actions, V, gamma)
+        if n_states is None:
+            n_states = self.nS - int(s_begin)
+        return self.engine.backup_range(int(s_begin), int(n_states), V, gamma)
+
+    def greedy(self, Q):
+        """(V, policy) = (max_a Q[s, a], first argmax) -- `max(q_sa)` / `np.argmax(q_sa)` of the classic planner loop."""
+        return self.engine.greedy(Q)
+
+    def value_iteration(self, gamma=1.0, eps=1e-2, max_iter=1000, slab=None):
+        """Synchronous value iteration over the whole state space on the device (only for envs whose nS values fit
+        in memory).  Stops when sum |V_new - V| <= eps (the classic gym loop).  Returns (V, policy, iterations)."""
+        torch = self._torch
+        nS = int(self.nS)
+        V = torch.zeros(nS, dtype=torch.float64, device=self.device)
+        slab = nS if slab is None else int(slab)
+        it = 0
+        for it in range(1, max_iter + 1):
+            V_new = torch.empty_like(V)
+            pi = torch.empty(nS, dtype=torch.int32, device=self.device)
+            for s0 in range(0, nS, slab):
+                n = min(slab, nS - s0)
+                v, p = self.engine.greedy(self.engine.backup_range(s0, n, V, gamma))
+                V_new[s0:s0 + n] = v
+                pi[s0:s0 + n] = p
+            delta = float((V_new - V).abs().sum().item())
+            V = V_new
+            if delta <= eps:
+                break
+        return V, pi, it
+
+    def predecessors(self, states):
+        """(row_ptr, pred_states): the CSR of `MapfEnv.predecessors` (reference mapf_env.py:373-376) per state."""
+        return self.engine.predecessors(states)
+
+    def project(self, states, agent_indexes):
+        """The joint states as `get_local_view(env, agent_indexes)` numbers them (reference utils.py:138-157)."""
+        return self.engine.project(states, agent_indexes)

@@ -155,6 +155,36 @@ int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *actions, in
                    uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
                    double *reward, double *prob, uint8_t *done, uint8_t *collision);
 
+/* ---- rows next to the hot path ------------------------------------------------------------------ */
+
+/* The consumer loop of a planner over the table, without materialising it:
+ *     Q[b] = 0;  for ((p, collision), s2, r, done) in P[states[b]][actions[b]]:  Q[b] += p * (r + gamma * V[s2])
+ * (mapf_env.py:448-479 provides P; the loop is the value-iteration backup gym-mapf's downstream planners run).
+ * Every operation is one IEEE binary64 operation in exactly this order (no fused multiply-add), so the result
+ * is bit-identical to the Python loop.  V is f64[v_len], indexed by the joint state: v_len >= nS is required and
+ * contexts whose states need two words are rejected (MAPF_ERR_UNSUPPORTED).  Q is f64[B]. */
+int mapf_backup(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, const double *V,
+                int64_t v_len, double gamma, double *Q, void *stream);
+/* The same for the slab [s_begin, s_begin + n_states) x [0, nA): Q[(s - s_begin) * nA + a]. */
+int mapf_backup_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_states, const double *V, int64_t v_len,
+                      double gamma, double *Q, void *stream);
+/* V_out[i] = max_a Q[i * nA + a], policy[i] = the first action attaining it (np.argmax); either output may be NULL. */
+int mapf_greedy(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy, void *stream);
+
+/* MapfEnv.predecessors (mapf_env.py:373-376, 414-434) for B states as CSR: row_len[b] = |predecessors(states[b])|;
+ * after mapf_scan_rows, pred[row_ptr[b] ..] holds the set (state_words * 8 bytes each, cartesian-product order with
+ * agent 0 slowest; the reference returns an unordered set). */
+int mapf_count_predecessors(const mapf_ctx *ctx, const void *states, int64_t B, int64_t *row_len, void *stream);
+int mapf_predecessors(const mapf_ctx *ctx, const void *states, int64_t B, const int64_t *row_ptr, void *pred,
+                      void *stream);
+
+/* get_local_view (utils.py:138-157) for states: out[b] = the joint state of the sub-env made of `agents` (HOST array
+ * of n_sub distinct agent indices, in the sub-env's agent order) that corresponds to states[b].  An output state has
+ * mapf_projected_words(ctx, n_sub) 64-bit words (1 when L**n_sub < 2**63, else 2). */
+int mapf_projected_words(const mapf_ctx *ctx, int32_t n_sub);
+int mapf_project_states(const mapf_ctx *ctx, const void *states, int64_t B, const int32_t *agents, int32_t n_sub,
+                        void *out_states, void *stream);
+
 const char *mapf_last_error(void);
 const char *mapf_version(void);
 

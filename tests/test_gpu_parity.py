@@ -356,3 +356,91 @@ def test_step_host_zero_copy_and_staged(name, torch):
                        env_offset=123)
         assert np.array_equal(out2[0].numpy(), dev[0].cpu().numpy())
         assert np.array_equal(out2[2].numpy().view(np.uint64), u64(dev[2]))
+
+
+# ---- rows next to the hot path ---------------------------------------------------------------------
+@pytest.mark.parametrize("name", G.names("backup_"))
+def test_backup_matches_reference(name, torch):
+    """k_backup vs the reference's own loop over env.P (fixtures from oracle/make_golden_next.py), bit for bit."""
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    V = torch.from_numpy(G.bits_to_f64(d["v_bits"]).copy()).to(eng.torch_device)
+    gamma = float(G.bits_to_f64(np.array([d["gamma_bits"]]))[0])
+    Q = eng.backup(states_tensor(eng, d["state_lo"], d["state_hi"]),
+                   torch.from_numpy(d["action"].astype(np.int32)).to(eng.torch_device), V, gamma)
+    assert np.array_equal(u64(Q), d["q_bits"])
+    if name.startswith("backup_c1"):  # the slab entry point on the complete table + greedy
+        Qr = eng.backup_range(0, eng.nS, V, gamma)
+        assert np.array_equal(u64(Qr).reshape(-1), d["q_bits"])
+        v, pi = eng.greedy(Qr)
+        want = G.bits_to_f64(d["q_bits"]).reshape(eng.nS, eng.nA)
+        assert np.array_equal(u64(v), G.f64_to_bits(want.max(axis=1)))
+        assert np.array_equal(pi.cpu().numpy(), want.argmax(axis=1).astype(np.int32))
+
+
+def test_backup_large_vs_oracle(torch):
+    """2 agents on empty-32-32 (2**20 states): a whole sweep against the C oracle, then value iteration end to end."""
+    spec, _ = G.load("rows_c5_n2")
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(77)
+    V = rng.normal(0, 30, eng.nS)
+    n_states, s0 = 3000, 517000
+    s = np.repeat(np.arange(s0, s0 + n_states, dtype=np.uint64), eng.nA)
+    a = np.tile(np.arange(eng.nA, dtype=np.int64), n_states)
+    want = ora.backup(s, np.zeros_like(s), a, V, 0.97)
+    got = eng.backup_range(s0, n_states, torch.from_numpy(V).to(eng.torch_device), 0.97)
+    assert np.array_equal(u64(got).reshape(-1), G.f64_to_bits(want))
+
+
+def test_value_iteration_c1(torch):
+    from gym_mapf_b200.envs.mapf_env import OptimizationCriteria
+    from gym_mapf_b200.envs.utils import create_mapf_env
+    from gym_mapf_b200.envs.vec_env import VecMapfEnv
+    env = create_mapf_env("empty-8-8", 1, 2, 0.2, -1000.0, 100.0, -1.0, OptimizationCriteria.Makespan, device=0)
+    vec = VecMapfEnv(env, 4)
+    V, pi, iters = vec.value_iteration(gamma=1.0, eps=1e-6, max_iter=200)
+    # the same sweeps with the C oracle
+    spec = dict(rows=["".join("@" if v else "." for v in r) for r in env.grid.obstacles], n_agents=2,
+                goals=[list(g) for g in env.agents_goals], fail_prob=0.2, r_clash=-1000.0, r_goal=100.0, r_living=-1.0,
+                soc=False)
+    ora = make_oracle(spec)
+    s = np.repeat(np.arange(env.nS, dtype=np.uint64), env.nA)
+    a = np.tile(np.arange(env.nA, dtype=np.int64), env.nS)
+    Vh = np.zeros(env.nS)
+    for _ in range(iters):
+        Vh = ora.backup(s, np.zeros_like(s), a, Vh, 1.0, threads=4).reshape(env.nS, env.nA).max(axis=1)
+    assert np.array_equal(u64(V), G.f64_to_bits(Vh))
+    assert iters < 200 and float(V[env.s]) > 0  # the start state is worth reaching the goal
+
+
+@pytest.mark.parametrize("name", G.names("preds_"))
+def test_predecessors_match_reference(name, torch):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    row_ptr, pred = eng.predecessors(states_tensor(eng, d["state_lo"], d["state_hi"]))
+    assert np.array_equal(row_ptr.cpu().numpy(), d["row_ptr"])
+    lo, hi = split_states(eng, pred)
+    for b in range(len(d["state_lo"])):  # the reference returns a set: compare sorted
+        sl = slice(int(d["row_ptr"][b]), int(d["row_ptr"][b + 1]))
+        got = np.sort((hi[sl].astype(object) << 64) | lo[sl].astype(object)) if eng.words == 2 else np.sort(lo[sl])
+        want = ((d["pred_hi"][sl].astype(object) << 64) | d["pred_lo"][sl].astype(object)) if eng.words == 2 \
+            else d["pred_lo"][sl]
+        assert np.array_equal(got, want), b
+
+
+@pytest.mark.parametrize("name", G.names("project_"))
+def test_projection_matches_reference(name, torch):
+    spec, d = G.load(name)
+    eng = make_engine(spec)
+    st = states_tensor(eng, d["state_lo"], d["state_hi"])
+    k = 0
+    while "agents_%d" % k in d:
+        out = eng.project(st, d["agents_%d" % k]).cpu().numpy().view(np.uint64)
+        if out.ndim == 1:
+            assert np.array_equal(out, d["proj_lo_%d" % k]) and not d["proj_hi_%d" % k].any()
+        else:
+            assert np.array_equal(out[:, 0], d["proj_lo_%d" % k]) and np.array_equal(out[:, 1], d["proj_hi_%d" % k])
+        k += 1
+    with pytest.raises(Exception):
+        eng.project(st, [0, 0])
