@@ -61,6 +61,7 @@ struct mapf_ctx {
     int threads = 256;           // CTA size of the hot kernels
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
+    size_t smem_backup = 0;      // smem_base + per-warp backup slabs
     int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout_tape = 0;
     int grid_expand = 0, grid_expand_range = 0, grid_plain = 0, grid_backup = 0, grid_backup_range = 0;
     KernelSet ks;
@@ -411,7 +412,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
     }
     const bool luts = sp.divL.fix == 0 &&
-                      MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.expand_slab_bytes <= smem_limit;
+                      MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.backup_slab_bytes <= smem_limit;
     if (!luts) ctx->threads = 256;
     sp.lut_smem = luts ? 1 : 0;
     {
@@ -445,6 +446,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     pick_kernels(n, sp.words, luts, &ctx->ks);
     ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
     ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
+    ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
     struct { const void *fn; size_t smem; int *grid; } plan[] = {
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
         {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
@@ -453,8 +455,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand},
         {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range},
-        {ctx->ks.backup, ctx->smem_expand, &ctx->grid_backup},
-        {ctx->ks.backup_range, ctx->smem_expand, &ctx->grid_backup_range}};
+        {ctx->ks.backup, ctx->smem_backup, &ctx->grid_backup},
+        {ctx->ks.backup_range, ctx->smem_backup, &ctx->grid_backup_range}};
     for (auto &pl : plan) {
         if (!pl.fn) continue;  // two-word states have no backup kernels
         if (pl.smem > 48 * 1024)
@@ -666,7 +668,7 @@ static int backup_impl(const mapf_ctx *ctx, bool range, const void *states, cons
     DevSpec sp = ctx->sp;
     void *args[] = {&sp, &states, &actions, &sb_lo, &B, &V, &gamma, &Q};
     const int grid = grid_for(B, ctx->threads, range ? ctx->grid_backup_range : ctx->grid_backup);
-    LAUNCH(range ? ctx->ks.backup_range : ctx->ks.backup, grid, ctx->threads, ctx->smem_expand, stream, args);
+    LAUNCH(range ? ctx->ks.backup_range : ctx->ks.backup, grid, ctx->threads, ctx->smem_backup, stream, args);
     return MAPF_OK;
 }
 

@@ -14,6 +14,7 @@ struct KernelSet {
     const void *backup = nullptr, *backup_range = nullptr;  // k_backup<N, LUTS, RANGE>; one-word states only
     const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;
     size_t expand_slab_bytes = 0;        // per warp
+    size_t backup_slab_bytes = 0;        // per warp
 };
 
 // words: 1 or 2; luts: move table staged in shared memory

@@ -28,6 +28,7 @@ static void fill(KernelSet *k) {
     k->pred_emit = (const void *)k_pred_emit<N, W>;
     k->project = (const void *)k_project<N, W>;
     k->expand_slab_bytes = sizeof(ExpandSlab<N>);
+    k->backup_slab_bytes = sizeof(BackupSlab<N>);
 }
 
 #define CAT_(a, b) a##b

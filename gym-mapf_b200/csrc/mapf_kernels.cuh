@@ -573,11 +573,18 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
 // =====================================================================================================
 //   Q[b] = 0; for ((p, collision), s2, r, done) in P[s_b][a_b]:  Q[b] += p * (r + gamma * V[s2])
 // with every operation a single IEEE binary64 operation, in the row's order -- what a planner's loop over
-// env.P[s][a] computes.  Rows are taken 32 at a time by a warp (phase A as in k_expand); phase B evaluates the
-// records of those rows 32 at a time, one per lane (the expensive part: outcome digits, conflict test, encode, the
-// gather of V), and then adds the 32 terms IN ORDER: every lane walks the window's terms through shuffles, so the
-// sum of a row is associated exactly like the sequential loop; lane i keeps row i's result and the warp stores its
-// 32 results in one coalesced segment.  Nothing but Q is written: the 25 B/record of the table never exist.
+// env.P[s][a] computes.  Rows are taken 32 at a time by a warp (phase A as in k_expand, lane = row); phase B
+// evaluates the records of those rows 32 at a time, one per lane (the expensive part: outcome digits, conflict
+// test, encode, the gather of V) and parks the 32 terms in shared memory; then lane i adds the terms that belong
+// to row i, in order, to its own accumulator.  The rows' sums run in parallel, each one associated exactly like the
+// sequential loop, and the warp stores its 32 results in one coalesced segment.  Nothing but Q is written: the
+// 25 B/record of the table never exist.
+template <int N>
+struct BackupSlab {
+    ExpandSlab<N> sl;
+    double term[32];
+};
+
 template <int N, bool LUTS, bool RANGE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
 k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, i64 B,
@@ -587,7 +594,8 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 lane_le = 0xffffffffu >> (31 - lane);
-    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
+    BackupSlab<N> &bs = reinterpret_cast<BackupSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
+    ExpandSlab<N> &sl = bs.sl;
     const i64 n_batches = (B + 31) >> 5;
     const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
     tables_wait<LUTS>(smem);
@@ -602,41 +610,35 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             if (lane >= o) incl += y;
         }
         const int total = (int)__shfl_sync(FULL, incl, 31);
-        const int myrel = (int)(incl - len);
+        const int myrel = (int)(incl - len), myend = (int)incl;  // my row's records: [myrel, myend)
         sl.pref[lane] = (u32)myrel;
         __syncwarp();
-        double acc = 0.0, mine = 0.0;  // acc: running sum of the current row (identical in every lane)
-        int cur = 0, rows_before = 0;  // cur: the row acc belongs to
+        double mine = 0.0;  // q = 0 (Python's sum starts from the int 0)
+        int rows_before = 0;
         for (int wrel = 0; wrel < total; wrel += 32) {
             const bool inwin = need && myrel >= wrel && myrel < wrel + 32;
             const u32 heads = __reduce_or_sync(FULL, inwin ? 1u << (myrel - wrel) : 0u);
             const int row = rows_before + __popc(heads & lane_le) - 1;
             rows_before += __popc(heads);
             const int rel = wrel + lane;
-            double term = 0.0;
             if (rel < total) {
                 const u32 flag = sl.flag[row];
+                double term;
                 if (flag & 1u) {  // the single record of a terminal state: (1.0, s, 0, True)
                     term = __dmul_rn(1.0, __dadd_rn(0.0, __dmul_rn(gamma, __ldg(V + sl.st[0][row]))));
                 } else {
                     const RecordOut rec = expand_record<N, 1>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row]);
                     term = __dmul_rn(rec.p, __dadd_rn(rec.reward, __dmul_rn(gamma, __ldg(V + rec.lo))));
                 }
+                bs.term[lane] = term;
             }
-            const int cnt = total - wrel < 32 ? total - wrel : 32;
-            for (int j = 0; j < cnt; ++j) {  // the ordered sum; `heads` bit j: a new row starts at term j
-                const double tj = __shfl_sync(FULL, term, j);
-                if (((heads >> j) & 1u) && (wrel + j) != 0) {
-                    if (lane == cur) mine = acc;
-                    acc = 0.0;
-                    ++cur;
-                }
-                acc = __dadd_rn(acc, tj);
-            }
+            __syncwarp();
+            // lane i: the terms of row i that fall in this window, in order
+            const int ja = (myrel > wrel ? myrel : wrel) - wrel, jb = (myend < wrel + 32 ? myend : wrel + 32) - wrel;
+            for (int j = ja; j < jb; ++j) mine = __dadd_rn(mine, bs.term[j]);
+            __syncwarp();
         }
-        if (lane == cur) mine = acc;
         if (need) Q[b] = mine;
-        __syncwarp();
     }
 }
 
