@@ -63,3 +63,45 @@ def combine(per_rank):
         for i, w in enumerate(words):
             total[i] = (total[i] + int(w)) & M64
     return dict(zip(CHECKSUM_KEYS, total))
+
+
+# ---- sharded value iteration: the one place with a real exchange step ------------------------------------------
+def all_gather_values(v_shard, shards, group=None):
+    """Every rank contributes the values of its own states; returns the full vector on every rank.  Shards may
+    differ in size by one (split_range), so the gather runs on shards padded to the largest and trims afterwards.
+    Backend-agnostic (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if len(shards) == 1 or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return v_shard
+    width = max(sh.count for sh in shards)
+    padded = torch.zeros(width, dtype=v_shard.dtype, device=v_shard.device)
+    padded[:v_shard.shape[0]] = v_shard
+    out = torch.empty(width * len(shards), dtype=v_shard.dtype, device=v_shard.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * width:r * width + sh.count] for r, sh in enumerate(shards)])
+
+
+def sharded_value_iteration(backup_and_greedy, n_states, world, rank, gamma=1.0, eps=1e-2, max_iter=1000, device="cpu",
+                            group=None):
+    """Synchronous value iteration with the state space cut into one contiguous shard per rank.
+    `backup_and_greedy(s_begin, count, V, gamma) -> (V_new_shard, policy_shard)` is the per-shard sweep (on the GPU:
+    `Engine.backup_range` + `Engine.greedy`).  Per sweep: local backup of the own shard against the full V, then ONE
+    all-gather of the new values (8 bytes per state) and one all-reduce of the change.  Returns (V, policy_shard,
+    iterations); every rank ends with the same, bit-identical V as a single-rank run."""
+    import torch
+    import torch.distributed as dist
+    shards = [split_range(n_states, world, r) for r in range(world)]
+    mine = shards[rank]
+    V = torch.zeros(n_states, dtype=torch.float64, device=device)
+    policy = None
+    it = 0
+    for it in range(1, max_iter + 1):
+        v_new, policy = backup_and_greedy(mine.begin, mine.count, V, gamma)
+        delta = (v_new - V[mine.begin:mine.begin + mine.count]).abs().sum().reshape(1)
+        V = all_gather_values(v_new, shards, group)
+        if world > 1:
+            dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+        if float(delta.item()) <= eps:
+            break
+    return V, policy, it
