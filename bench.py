@@ -204,9 +204,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version / debug lines to stdout when NCCL_DEBUG is set: keep stdout for the one JSON line by
+        # pointing file descriptor 1 at stderr while the communicator comes up (first collective included)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     env = make_env(device=local)
     eng = env.engine
     B, K, W = ENVS_PER_GPU, args.steps, args.warmup

@@ -19,7 +19,7 @@ FLAG_DONE, FLAG_COLLISION = 1, 2
 EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
            "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_rollout", "mapf_step_host",
-           "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_count_predecessors", "mapf_predecessors",
+           "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_greedy_bcast", "mapf_count_predecessors", "mapf_predecessors",
            "mapf_projected_words", "mapf_project_states", "mapf_last_error", "mapf_version"]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.mapf_backup.argtypes = [vp, vp, vp, i64, vp, i64, C.c_double, vp, vp]
         L.mapf_backup_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, i64, C.c_double, vp, vp]
         L.mapf_greedy.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mapf_greedy_bcast.argtypes = [vp, vp, i64, i64, C.POINTER(vp), i32, vp, vp]
         L.mapf_count_predecessors.argtypes = [vp, vp, i64, vp, vp]
         L.mapf_predecessors.argtypes = [vp, vp, i64, vp, vp, vp]
         L.mapf_projected_words.argtypes = [vp, i32]
@@ -333,6 +334,18 @@ class Engine:
         pi = torch.empty(n_states, dtype=torch.int32, device=self.torch_device)
         check(lib().mapf_greedy(self._h, _ptr(Q), n_states, _ptr(V), _ptr(pi), self._stream()))
         return V, pi
+
+    def greedy_bcast(self, Q, s_begin, peer_ptrs):
+        """Greedy step of a SHARDED sweep with the exchange fused in: V of state s_begin + i goes straight into every
+        rank's value vector (`peer_ptrs`: device addresses of all ranks' vectors, e.g. a symmetric-memory handle's
+        buffer_ptrs).  Returns the policy of the shard."""
+        import torch
+        n_states = Q.shape[0]
+        pi = torch.empty(n_states, dtype=torch.int32, device=self.torch_device)
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        check(lib().mapf_greedy_bcast(self._h, _ptr(Q), n_states, int(s_begin), arr, len(peer_ptrs), _ptr(pi),
+                                      self._stream()))
+        return pi
 
     def predecessors(self, states):
         """CSR (row_ptr, pred_states) of MapfEnv.predecessors for every state."""

@@ -689,15 +689,37 @@ extern "C" int mapf_backup_range(const mapf_ctx *ctx, const uint64_t s_begin[2],
     return backup_impl(ctx, true, nullptr, nullptr, s_begin[0], B, V, v_len, gamma, Q, stream);
 }
 
-extern "C" int mapf_greedy(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy,
-                           void *stream) {
-    if (!ctx || n_states < 0 || (n_states > 0 && !Q)) return fail(MAPF_ERR_INVALID, "mapf_greedy: bad argument");
+static int greedy_impl(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy,
+                       const PeerList &peers, int64_t s_begin, void *stream) {
     if (n_states == 0) return MAPF_OK;
     DeviceGuard g(ctx->device);
     const int64_t nA = (int64_t)ctx->sp.nA;
-    k_greedy<<<grid_for(n_states * 32, 256, ctx->grid_plain), 256, 0, (cudaStream_t)stream>>>(Q, n_states, nA, V_out, policy);
+    k_greedy<<<grid_for(((n_states + 31) / 32) * 32, 256, ctx->grid_plain), 256, 0, (cudaStream_t)stream>>>(
+        Q, n_states, nA, V_out, policy, peers, s_begin);
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
+}
+
+extern "C" int mapf_greedy(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy,
+                           void *stream) {
+    if (!ctx || n_states < 0 || (n_states > 0 && !Q)) return fail(MAPF_ERR_INVALID, "mapf_greedy: bad argument");
+    PeerList none;
+    memset(&none, 0, sizeof(none));
+    return greedy_impl(ctx, Q, n_states, V_out, policy, none, 0, stream);
+}
+
+extern "C" int mapf_greedy_bcast(const mapf_ctx *ctx, const double *Q, int64_t n_states, int64_t s_begin,
+                                 double *const *peer_values, int32_t n_peers, int32_t *policy, void *stream) {
+    if (!ctx || n_states < 0 || s_begin < 0 || !peer_values || n_peers < 1 || n_peers > 16 || (n_states > 0 && !Q))
+        return fail(MAPF_ERR_INVALID, "mapf_greedy_bcast: bad argument (1..16 peers)");
+    PeerList peers;
+    memset(&peers, 0, sizeof(peers));
+    peers.n = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_values[r]) return fail(MAPF_ERR_INVALID, "mapf_greedy_bcast: NULL peer pointer %d", r);
+        peers.ptr[r] = peer_values[r];
+    }
+    return greedy_impl(ctx, Q, n_states, nullptr, policy, peers, s_begin, stream);
 }
 
 extern "C" int mapf_count_predecessors(const mapf_ctx *ctx, const void *states, int64_t B, int64_t *row_len, void *stream) {

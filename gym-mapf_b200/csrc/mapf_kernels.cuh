@@ -642,28 +642,49 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     }
 }
 
-// V[s] = max_a Q[s][a], policy[s] = the first a that attains it (np.argmax); one warp per state.
+// V[s] = max_a Q[s][a], policy[s] = the first a that attains it (np.argmax).  A warp takes 32 consecutive states
+// (lanes stride over the actions of one state at a time, lane i keeps state i's result), so V and the policy are
+// written in coalesced segments.
+// Fused exchange step of sharded value iteration: with `peers.n > 0` the new values are written straight into EVERY
+// rank's copy of the value vector (`peers.ptr[r]` are peer-mapped device pointers, NVLink stores), at the states'
+// global positions `s_begin + i` -- the all-gather of the sweep happens inside this kernel, segment by segment,
+// instead of as a separate collective after it.
+struct PeerList {
+    double *ptr[16];
+    int n;
+};
+
 static __global__ void __launch_bounds__(256)
-k_greedy(const double *__restrict__ Q, i64 n_states, i64 nA, double *__restrict__ V_out, int *__restrict__ policy) {
+k_greedy(const double *__restrict__ Q, i64 n_states, i64 nA, double *__restrict__ V_out, int *__restrict__ policy,
+         PeerList peers, i64 s_begin) {
     const int lane = threadIdx.x & 31;
     const i64 warps = (i64)gridDim.x * (blockDim.x >> 5);
-    for (i64 s = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < n_states; s += warps) {
-        const double *q = Q + s * nA;
-        double best = 0.0;
-        i64 arg = -1;
-        for (i64 a = lane; a < nA; a += 32) {
-            const double v = q[a];
-            if (arg < 0 || v > best) { best = v; arg = a; }  // strictly greater: the first maximum stays
-        }
+    const i64 n_groups = (n_states + 31) >> 5;
+    for (i64 grp = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); grp < n_groups; grp += warps) {
+        double keep_v = 0.0;
+        int keep_a = 0;
+        const i64 s0 = grp << 5;
+        const int cnt = n_states - s0 < 32 ? (int)(n_states - s0) : 32;
+        for (int i = 0; i < cnt; ++i) {
+            const double *q = Q + (s0 + i) * nA;
+            double best = 0.0;
+            i64 arg = -1;
+            for (i64 a = lane; a < nA; a += 32) {
+                const double v = q[a];
+                if (arg < 0 || v > best) { best = v; arg = a; }  // strictly greater: the first maximum stays
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const i64 oa = __shfl_xor_sync(0xffffffffu, arg, o);
-            if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const i64 oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) { best = ob; arg = oa; }
+            }
+            if (lane == i) { keep_v = best; keep_a = (int)arg; }
         }
-        if (lane == 0) {
-            if (V_out) V_out[s] = best;
-            if (policy) policy[s] = (int)arg;
+        if (lane < cnt) {
+            if (V_out) V_out[s0 + lane] = keep_v;
+            if (policy) policy[s0 + lane] = keep_a;
+            for (int r = 0; r < peers.n; ++r) peers.ptr[r][s_begin + s0 + lane] = keep_v;
         }
     }
 }

@@ -171,6 +171,13 @@ int mapf_backup_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_
 /* V_out[i] = max_a Q[i * nA + a], policy[i] = the first action attaining it (np.argmax); either output may be NULL. */
 int mapf_greedy(const mapf_ctx *ctx, const double *Q, int64_t n_states, double *V_out, int32_t *policy, void *stream);
 
+/* The exchange step of SHARDED value iteration fused into the same kernel: the new value of state s_begin + i is
+ * written straight into every rank's copy of the value vector, peer_values[r][s_begin + i] (HOST array of n_peers
+ * device pointers, the other ranks' being peer-mapped over NVLink, e.g. torch symmetric memory), instead of a
+ * separate all-gather after the sweep.  The caller synchronises the ranks before the vector is read again. */
+int mapf_greedy_bcast(const mapf_ctx *ctx, const double *Q, int64_t n_states, int64_t s_begin, double *const *peer_values,
+                      int32_t n_peers, int32_t *policy, void *stream);
+
 /* MapfEnv.predecessors (mapf_env.py:373-376, 414-434) for B states as CSR: row_len[b] = |predecessors(states[b])|;
  * after mapf_scan_rows, pred[row_ptr[b] ..] holds the set (state_words * 8 bytes each, cartesian-product order with
  * agent 0 slowest; the reference returns an unordered set). */
