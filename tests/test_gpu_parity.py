@@ -444,3 +444,20 @@ def test_projection_matches_reference(name, torch):
         k += 1
     with pytest.raises(Exception):
         eng.project(st, [0, 0])
+
+
+def test_greedy_bcast_single_peer(torch):
+    """The fused exchange step with one 'peer' (the local vector): values land at their global positions."""
+    spec, d = G.load("backup_obst4_n2")
+    eng = make_engine(spec)
+    rng = np.random.default_rng(5)
+    n_states, s_begin = 57, 40
+    Q = torch.from_numpy(rng.normal(0, 5, (n_states, eng.nA))).to(eng.torch_device)
+    Q[3, 7] = Q[3, 2] = Q[3].max() + 1.0  # a tie: the first maximum wins
+    v, pi = eng.greedy(Q)
+    full = torch.full((eng.nS,), -1.0, dtype=torch.float64, device=eng.torch_device)
+    pi2 = eng.greedy_bcast(Q, s_begin, [full.data_ptr()])
+    assert torch.equal(pi, pi2) and int(pi[3]) == 2
+    assert torch.equal(full[s_begin:s_begin + n_states], v)
+    assert bool((full[:s_begin] == -1).all()) and bool((full[s_begin + n_states:] == -1).all())
+    assert torch.equal(v, Q.max(dim=1).values)
