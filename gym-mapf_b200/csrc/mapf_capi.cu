@@ -271,6 +271,20 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         const u64 ll = (u64)L * (u64)L;
         sp.LL = (u32)ll;
         sp.divLL = make_fastdiv(ll);
+        // two-word states: split point of the decode / encode (see DevSpec::split_ok)
+        sp.split_ok = 0;
+        if (sp.words == 2 && n >= 2) {
+            const int klo = MAPF_SPLIT_KLO(n) < n ? MAPF_SPLIT_KLO(n) : n - 1;
+            u128 D = 1, hi_span = 1;
+            bool fits = true;
+            for (int i = 0; i < klo; ++i) { D *= (u128)L; fits = fits && D < ((u128)1 << 63); }
+            for (int i = klo; i < n; ++i) { hi_span *= (u128)L; fits = fits && hi_span < ((u128)1 << 49); }
+            if (fits) {
+                sp.split_ok = 1;
+                sp.splitD = (u64)D;
+                sp.invD = 1.0 / (double)(u64)D;
+            }
+        }
         sp.divL = make_div32((u32)L);
         u128 v = nS - 1;
         for (int pass = 0; pass < 8; ++pass) {

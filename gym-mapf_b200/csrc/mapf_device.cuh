@@ -72,6 +72,13 @@ struct DevSpec {
     u64 nA;            // 5**n
     u64 smax[2];       // nS - 1
     FastDiv divLL;     // division by L*L
+    // Two-word states: s = q * D + r with D = L**KLO(n) splits the digits into a low and a high group that are then
+    // decoded independently with one-word arithmetic (split_ok: D < 2**63 and L**(n - KLO) < 2**49, so that one fp64
+    // estimate of q is off by at most one).  Otherwise: long division over 32-bit limbs.
+    int split_ok;
+    int pad2;
+    u64 splitD;
+    double invD;
     Div32 divL;        // division by L of a two-digit chunk
     u64 s0[2];         // start state
     u64 sgoal[2];      // locations_to_state(agents_goals)
@@ -113,23 +120,62 @@ __device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &
 // ---- joint state <-> per-agent cells: little-endian radix L, agent 0 least significant (__init__.py:50-79) ----
 // The state is split into two-digit chunks (radix L*L < 2**32) with 64-bit divisions and each chunk into its two
 // digits with one 32-bit multiply-high division.
+// number of low digits of the two-word split for n agents: 2 * ceil(n / 4)
+#define MAPF_SPLIT_KLO(n) (2 * (((n) + 3) / 4))
+
+// digits of a one-word value, two at a time: chunk = x mod L*L by one 64-bit magic division, then chunk / L
+template <int N, bool EXACT>
+__device__ __forceinline__ void decode_word(const DevSpec &sp, u64 x, int *cell) {
+    constexpr int PAIRS = (N + 1) / 2;
+    u32 chunk[PAIRS];
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) {
+        if (p + 1 < PAIRS) {
+            const u64 q = fastdiv(x, sp.divLL);
+            chunk[p] = (u32)x - (u32)q * sp.LL;
+            x = q;
+        } else {
+            chunk[p] = (u32)x;
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) {
+        if (2 * p + 1 < N) {
+            u32 q, r;
+            divmod_L<EXACT>(sp, chunk[p], q, r);
+            cell[2 * p] = (int)r;
+            cell[2 * p + 1] = (int)q;
+        } else {
+            cell[2 * p] = (int)chunk[p];
+        }
+    }
+}
+
 template <int N, int WORDS, bool EXACT = false>
 __device__ __forceinline__ void decode_state(const DevSpec &sp, u64 lo, u64 hi, int (&cell)[N]) {
     constexpr int PAIRS = (N + 1) / 2;
+    constexpr int KLO = MAPF_SPLIT_KLO(N) < N ? MAPF_SPLIT_KLO(N) : N - 1;
     u32 chunk[PAIRS];
-    if (WORDS == 1) {
-        u64 x = lo;
+    if constexpr (WORDS == 1) {
+        decode_word<N, EXACT>(sp, lo, cell);
+        cell[N - 1] = (int)min((u32)cell[N - 1], (u32)(sp.L - 1));
+        return;
+    }
+    if constexpr (WORDS == 2 && N >= 4) if (sp.split_ok) {  // kernel-uniform
+        // q = floor(s / D) from one fp64 estimate (q < 2**49: the rounded product is floor or floor + 1), fixed
+        // with the sign of the remainder, whose low 64 bits are all that is needed (|r| < D < 2**63)
+        const double d = __fma_rn(__ull2double_rn(hi), 18446744073709551616.0, __ull2double_rn(lo));
+        u64 q = __double2ull_rn(__dmul_rn(d, sp.invD));
+        i64 r = (i64)(lo - q * sp.splitD);
+        if (r < 0) { r += (i64)sp.splitD; q -= 1; }
+        decode_word<KLO, EXACT>(sp, (u64)r, &cell[0]);
+        decode_word<(N - KLO > 0 ? N - KLO : 1), EXACT>(sp, q, &cell[KLO < N ? KLO : 0]);
+        // an out-of-range state (rejected by the host API) must still give valid table indices
 #pragma unroll
-        for (int p = 0; p < PAIRS; ++p) {
-            if (p + 1 < PAIRS) {
-                const u64 q = fastdiv(x, sp.divLL);
-                chunk[p] = (u32)x - (u32)q * sp.LL;
-                x = q;
-            } else {
-                chunk[p] = (u32)x;
-            }
-        }
-    } else {
+        for (int i = 0; i < N; ++i) cell[i] = (int)min((u32)cell[i], (u32)(sp.L - 1));
+        return;
+    }
+    {
         // 128-bit / LL long division over 32-bit limbs; a partial dividend (rem << 32 | limb) fits 64 bits
         u32 limb[4] = {(u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32)};
 #pragma unroll
@@ -167,24 +213,48 @@ __device__ __forceinline__ void decode_state(const DevSpec &sp, u64 lo, u64 hi, 
     cell[N - 1] = (int)min((u32)cell[N - 1], (u32)(sp.L - 1));
 }
 
+// Horner over two-digit chunks in one word
+template <int N>
+__device__ __forceinline__ u64 encode_word(const DevSpec &sp, const int *cell) {
+    constexpr int PAIRS = (N + 1) / 2;
+    const u32 L = (u32)sp.L;
+    u64 acc = 0;
+#pragma unroll
+    for (int p = PAIRS - 1; p >= 0; --p) {
+        const u32 chunk = (2 * p + 1 < N) ? (u32)cell[2 * p + 1] * L + (u32)cell[2 * p] : (u32)cell[2 * p];
+        acc = acc * sp.LL + chunk;
+    }
+    return acc;
+}
+
 template <int N, int WORDS>
 __device__ __forceinline__ void encode_state(const DevSpec &sp, const int (&cell)[N], u64 &lo, u64 &hi) {
     constexpr int PAIRS = (N + 1) / 2;
+    constexpr int KLO = MAPF_SPLIT_KLO(N) < N ? MAPF_SPLIT_KLO(N) : N - 1;
+    if constexpr (WORDS == 1) {
+        lo = encode_word<N>(sp, &cell[0]);
+        hi = 0;
+        return;
+    }
+    if constexpr (WORDS == 2 && N >= 4) if (sp.split_ok) {  // kernel-uniform: low and high digit groups in one word each
+        const u64 vlo = encode_word<KLO>(sp, &cell[0]);
+        const u64 vhi = encode_word<(N - KLO > 0 ? N - KLO : 1)>(sp, &cell[KLO < N ? KLO : 0]);
+        const u64 plo = vhi * sp.splitD;
+        lo = plo + vlo;
+        hi = __umul64hi(vhi, sp.splitD) + (lo < plo ? 1ull : 0ull);
+        return;
+    }
     const u32 L = (u32)sp.L;
     u64 alo = 0, ahi = 0;
 #pragma unroll
     for (int p = PAIRS - 1; p >= 0; --p) {
         const u32 chunk = (2 * p + 1 < N) ? (u32)cell[2 * p + 1] * L + (u32)cell[2 * p] : (u32)cell[2 * p];
-        if (WORDS == 1) {
-            alo = alo * sp.LL + chunk;
-        } else {
-            const u64 carry = __umul64hi(alo, (u64)sp.LL);
-            ahi = ahi * sp.LL + carry;
-            alo = alo * sp.LL;
-            const u64 t = alo + chunk;
-            ahi += (t < alo) ? 1ull : 0ull;
-            alo = t;
-        }
+        const u64 carry = __umul64hi(alo, (u64)sp.LL);
+        ahi = ahi * sp.LL + carry;
+        alo = alo * sp.LL;
+        const u64 t = alo + chunk;
+        ahi += (t < alo) ? 1ull : 0ull;
+        alo = t;
     }
     lo = alo;
     hi = ahi;
