@@ -461,3 +461,108 @@ def test_greedy_bcast_single_peer(torch):
     assert torch.equal(full[s_begin:s_begin + n_states], v)
     assert bool((full[:s_begin] == -1).all()) and bool((full[s_begin + n_states:] == -1).all())
     assert torch.equal(v, Q.max(dim=1).values)
+
+
+# ---- BASELINE.json's full sizes through size-independent properties ---------------------------------------------------
+def _c4_engine():
+    from gym_mapf_b200.envs.mapf_env import OptimizationCriteria
+    from gym_mapf_b200.envs.utils import create_mapf_env
+    env = create_mapf_env("room-64-64-8", 1, 8, 0.2, -1000.0, 100.0, -1.0, OptimizationCriteria.Makespan, device=0)
+    return env, env.engine
+
+
+def test_c4_full_size_step_properties(torch):
+    """16 M envs, 8 agents, 128-bit states (BASELINE configs[3]): the vectorised and the scalar kernel variants agree,
+    a batch stepped in two shards with the right env offsets equals the batch stepped whole (disjoint Philox
+    streams), every next state is inside the state space, terminal states are fixed points with reward 0 / prob 0."""
+    env, eng = _c4_engine()
+    B = 1 << 24
+    dev = eng.torch_device
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    cells = torch.randint(0, eng.L, (B, eng.n), generator=g, device=dev, dtype=torch.int32)
+    cells[:1000, 1] = cells[:1000, 0]  # some already-clashed (terminal) states
+    states = eng.encode(cells)
+    actions = torch.randint(0, eng.nA, (B,), generator=g, device=dev, dtype=torch.int32)
+    whole = eng.step(states, actions, seed=11, step_index=4)
+    ns, reward, prob, done, coll = whole
+    # (a) scalar variant: an odd batch on misaligned views takes the one-env-per-thread kernel
+    part = eng.step(states[1:B - 2], actions[1:B - 2], seed=11, step_index=4, env_offset=1)
+    for a, b in zip(whole, part):
+        assert torch.equal(a[1:B - 2], b)
+    # (b) two shards == whole
+    h = B // 2
+    lo_half = eng.step(states[:h], actions[:h], seed=11, step_index=4, env_offset=0)
+    hi_half = eng.step(states[h:], actions[h:], seed=11, step_index=4, env_offset=h)
+    for a, b, c in zip(whole, lo_half, hi_half):
+        assert torch.equal(a[:h], b) and torch.equal(a[h:], c)
+    # (c) range and terminal fixed points
+    back = eng.decode(ns)
+    assert int(back.min()) >= 0 and int(back.max()) < eng.L
+    assert torch.equal(eng.encode(back), ns)
+    assert torch.equal(ns[:1000], states[:1000]) and bool(done[:1000].all()) and not bool(coll[:1000].any())
+    assert float(reward[:1000].abs().max()) == 0.0 and float(prob[:1000].abs().max()) == 0.0
+    # (d) a collision always ends the episode; probabilities are products of {0.8, 0.1, 0.9, 1.0, 0.2}
+    assert bool(done[coll].all())
+    assert float(prob.min()) >= 0.0 and float(prob.max()) <= 1.0
+    zero = prob == 0.0  # exactly the steps from a terminal state (two agents on one cell): no-ops
+    srt = cells.sort(dim=1).values
+    dup = (srt[:, 1:] == srt[:, :-1]).any(dim=1)
+    assert torch.equal(zero, dup)
+    assert torch.equal(ns[zero], states[zero]) and bool(done[zero].all()) and float(reward[zero].abs().max()) == 0.0
+
+
+def test_c2_full_size_expand_properties(torch):
+    """2**20 random (s, a) rows of C2 (36 M records): every row's probabilities add up to 1, row lengths are
+    products of 1/2/3, collision implies done, and the checksums equal the C oracle's on the same rows."""
+    spec, _ = G.load("rows_c2")
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    B = 1 << 20
+    rng = np.random.default_rng(8)
+    cells = rng.integers(0, eng.L, (B, eng.n)).astype(np.int32)
+    lo, hi = ora.encode(cells)
+    a = rng.integers(0, eng.nA, B).astype(np.int64)
+    row_ptr, ns, prob, reward, flags = eng.transitions(states_tensor(eng, lo, hi),
+                                                       torch.from_numpy(a.astype(np.int32)).to(eng.torch_device))
+    lens = (row_ptr[1:] - row_ptr[:-1])
+    assert int(lens.min()) >= 1 and int(lens.max()) <= 81
+    seg = torch.repeat_interleave(torch.arange(B, device=eng.torch_device), lens)
+    sums = torch.zeros(B, dtype=torch.float64, device=eng.torch_device).index_add_(0, seg, prob)
+    assert float((sums - 1.0).abs().max()) < 1e-12
+    assert bool(((flags & 2) == 0).logical_or((flags & 1) == 1).all())
+    got = eng.checksum(ns, prob, reward, flags).cpu().numpy().view(np.uint64)
+    want = ora.rows(lo, hi, a, threads=8)
+    cs = G.checksums(want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]), G.f64_to_bits(want["reward"]),
+                     want["done"], want["collision"])
+    assert [int(x) for x in got] == [cs[k] for k in ("count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi",
+                                                     "sum_prob_bits", "sum_reward_bits", "ordered")]
+
+
+def test_thirteen_agents(torch):
+    """The largest supported agent count (5**13 joint actions, rows of up to 3**13 records) on a small grid."""
+    rows = ["....", ".@..", "...."]
+    starts = [[r, c] for r in range(3) for c in range(4) if not (r == 1 and c == 1)] + [[0, 0], [2, 3]]
+    goals = list(reversed(starts))
+    spec = dict(rows=rows, n_agents=13, starts=starts, goals=goals, fail_prob=0.2, r_clash=-1000.0, r_goal=100.0,
+                r_living=-1.0, soc=True)
+    eng = make_engine(spec)
+    ora = make_oracle(spec)
+    rng = np.random.default_rng(13)
+    cells = np.stack([rng.permutation(11)[:11].tolist() + rng.integers(0, 11, 2).tolist() for _ in range(6)]).astype(np.int32)
+    cells[0] = np.arange(13) % 11          # duplicates: terminal
+    cells[1, :11] = np.arange(11)          # 11 distinct + 2 random
+    lo, hi = ora.encode(cells)
+    a = rng.integers(0, eng.nA, 6).astype(np.int64)
+    a[2] = 0                               # everybody stays: a single outcome
+    want = ora.rows(lo, hi, a)
+    got = eng.transitions(states_tensor(eng, lo, hi), torch.from_numpy(a.astype(np.int32)).to(eng.torch_device))
+    assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                      G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+    uni = rng.random((6, 13))
+    ws = ora.step(lo, hi, a, uni)
+    ns, reward, prob, done, coll = eng.step(states_tensor(eng, lo, hi), torch.from_numpy(a.astype(np.int32)).to(eng.torch_device),
+                                            uniforms=torch.from_numpy(uni).to(eng.torch_device))
+    glo, ghi = split_states(eng, ns)
+    assert np.array_equal(glo, ws["next_lo"]) and np.array_equal(ghi, ws["next_hi"])
+    assert np.array_equal(u64(prob), G.f64_to_bits(ws["prob"])) and np.array_equal(u64(reward), G.f64_to_bits(ws["reward"]))
