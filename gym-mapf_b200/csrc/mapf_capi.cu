@@ -80,6 +80,8 @@ struct mapf_ctx {
     cudaStream_t hs[2] = {nullptr, nullptr};
     unsigned char *d_stage = nullptr;
     size_t d_stage_bytes = 0;
+    unsigned char *h_small = nullptr;   // page-locked scratch of the small-batch host step (mapped into the device)
+    unsigned char *h_small_dev = nullptr;
 };
 
 static bool pick_kernels(int n, int words, bool luts, KernelSet *ks) {
@@ -154,6 +156,7 @@ extern "C" void mapf_ctx_destroy(mapf_ctx *ctx) {
         cudaFree(ctx->d_colbits);
         cudaFree(ctx->d_colbase);
         cudaFree(ctx->d_stage);
+        if (ctx->h_small) cudaFreeHost(ctx->h_small);
         for (int i = 0; i < 2; ++i)
             if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
     }
@@ -800,6 +803,7 @@ static PhiloxKeys make_keys(uint64_t seed) {
     return K;
 }
 
+#define MAPF_SMALL_HOST_BATCH 1024         // mapf_step_host: batches up to this size go through the pinned scratch
 #define MAPF_LAUNCH_MAX_ENVS (1ll << 30)  // kernels index envs with 32 bits; larger batches are split
 
 // Picks the step-kernel variant: replayed uniforms -> TAPE; otherwise the 2-envs-per-thread kernel with 128-bit
@@ -924,6 +928,33 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
     const size_t sw = (size_t)ctx->sp.words * 8;
     for (int i = 0; i < 2; ++i)
         if (!ctx->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
+    // Small batches (the scalar MapfEnv.step is B = 1): the fixed cost of eight staged copies dwarfs the work.  Pack
+    // the inputs into the context's page-locked scratch, run the kernel directly on its device mapping (zero copy),
+    // unpack: one launch and one synchronisation.
+    if (B <= MAPF_SMALL_HOST_BATCH) {
+        const size_t cap = MAPF_SMALL_HOST_BATCH;
+        const size_t o_s = 0, o_a = o_s + 16 * cap, o_u = o_a + 4 * cap, o_ns = o_u + 8 * MAPF_MAXN * cap,
+                     o_r = o_ns + 16 * cap, o_p = o_r + 8 * cap, o_d = o_p + 8 * cap, o_c = o_d + cap, total = o_c + cap;
+        if (!ctx->h_small) {
+            CUDA_TRY(cudaHostAlloc((void **)&ctx->h_small, total, cudaHostAllocMapped));
+            CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->h_small_dev, ctx->h_small, 0));
+        }
+        unsigned char *h = ctx->h_small, *d = ctx->h_small_dev;
+        memcpy(h + o_s, states, sw * B);
+        memcpy(h + o_a, actions, 4 * (size_t)B);
+        if (uniforms) memcpy(h + o_u, uniforms, (size_t)n * 8 * B);
+        int rc = launch_step(ctx, d + o_s, (const int32_t *)(d + o_a), B, uniforms ? (const double *)(d + o_u) : nullptr, seed,
+                             step_index, env_offset, options, d + o_ns, (double *)(d + o_r), (double *)(d + o_p), d + o_d,
+                             d + o_c, ctx->hs[0]);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
+        memcpy(next_states, h + o_ns, sw * B);
+        memcpy(reward, h + o_r, 8 * (size_t)B);
+        memcpy(prob, h + o_p, 8 * (size_t)B);
+        memcpy(done, h + o_d, (size_t)B);
+        memcpy(collision, h + o_c, (size_t)B);
+        return MAPF_OK;
+    }
     // Zero-copy path: when every buffer is page-locked host memory that the device can address (cudaHostAlloc /
     // cudaHostRegister, e.g. torch's pin_memory()), ONE launch of the step kernel reads the inputs and writes the
     // results straight over PCIe -- both directions stream concurrently, with no staging copies and no per-copy

@@ -104,6 +104,7 @@ def _gym_np_random(seed):
 class MapfEnv(_EnvBase):
     # rows of P fetched per state when nA * 3**n stays below this many records, else one (s, a) row at a time
     _PREFETCH_RECORDS = 1 << 21
+    _PREFETCH_STATES = 64
     _CACHE_STATES = 2048
 
     def __init__(self, grid: MapfGrid, n_agents: int, start_locations: tuple, goal_locations: tuple, fail_prob: float,
@@ -157,6 +158,7 @@ class MapfEnv(_EnvBase):
         new.__dict__.update(self.__dict__)
         new.P = function_to_get_item_of_object(new._partial_get_transitions)
         new._rows = collections.OrderedDict()
+        new.__dict__.pop("_step_buf", None)
         return new
 
     # ---- encodings (host scalars; the bulk versions are VecMapfEnv.state_to_cells / cells_to_state) ---------
@@ -245,8 +247,14 @@ class MapfEnv(_EnvBase):
             raise IndexError("state %d / action %d outside [0, %d) x [0, %d)" % (s, a, self.nS, self.nA))
         eng = self.engine
         if self.nA * eng.max_row_len <= self._PREFETCH_RECORDS:
-            row_ptr, ns, prob, reward, flags = self._fetch(s, lambda: self._host_csr(eng.table_range(s, 1)))
-            lo, hi = int(row_ptr[a]), int(row_ptr[a + 1])
+            # a block of consecutive states per GPU call (planners sweep s in order): one launch sequence and one
+            # read-back serve up to _PREFETCH_STATES states
+            k = max(1, min(self._PREFETCH_STATES, self._PREFETCH_RECORDS // (self.nA * eng.max_row_len)))
+            s0 = s - s % k
+            n_states = min(k, self.nS - s0)
+            row_ptr, ns, prob, reward, flags = self._fetch(("block", s0), lambda: self._host_csr(eng.table_range(s0, n_states)))
+            row = (s - s0) * self.nA + a
+            lo, hi = int(row_ptr[row]), int(row_ptr[row + 1])
         else:
             def one_row():
                 import torch
@@ -263,18 +271,26 @@ class MapfEnv(_EnvBase):
         are drawn here from `self.np_random`, one per agent in agent order and none for a terminal state, so the
         random stream is consumed exactly as the reference consumes it."""
         eng = self.engine
+        buf = self.__dict__.get("_step_buf")
+        if buf is None:  # reused across calls: the scalar path is dominated by fixed costs
+            buf = self._step_buf = dict(
+                state=np.zeros(eng.words, np.uint64), action=np.zeros(1, np.int32),
+                uniforms=np.zeros(self.n_agents, np.float64),
+                out=(np.zeros(eng.words, np.uint64), np.zeros(1, np.float64), np.zeros(1, np.float64),
+                     np.zeros(1, np.uint8), np.zeros(1, np.uint8)))
         terminal = self.is_terminal(self.state_to_locations(self.s))
+        uniforms = buf["uniforms"]
         if terminal:
-            uniforms = np.zeros(self.n_agents, dtype=np.float64)
+            uniforms[:] = 0.0
         else:
-            uniforms = np.array([self.np_random.rand() for _ in range(self.n_agents)], dtype=np.float64)
-        m = (1 << 64) - 1
-        state = np.array([self.s & m, (self.s >> 64) & m][:eng.words], dtype=np.uint64)
-        action = np.array([a % self.nA], dtype=np.int32)
-        out = (np.zeros(eng.words, np.uint64), np.zeros(1, np.float64), np.zeros(1, np.float64), np.zeros(1, np.uint8),
-               np.zeros(1, np.uint8))
-        eng.step_host(state, action, out, uniforms=uniforms)
-        ns, reward, prob, done, coll = out
+            uniforms[:] = self.np_random.random_sample(self.n_agents)  # n successive rand() draws, in agent order
+        state = buf["state"]
+        state[0] = self.s & 0xFFFFFFFFFFFFFFFF
+        if eng.words == 2:
+            state[1] = self.s >> 64
+        buf["action"][0] = a % self.nA
+        ns, reward, prob, done, coll = buf["out"]
+        eng.step_host(state, buf["action"], buf["out"], uniforms=uniforms)
         new_state = int(ns[0]) | (int(ns[1]) << 64 if eng.words == 2 else 0)
         self.lastaction = a
         if terminal:
