@@ -274,6 +274,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         const u64 ll = (u64)L * (u64)L;
         sp.LL = (u32)ll;
         sp.divLL = make_fastdiv(ll);
+        sp.invLL = 1.0 / (double)ll;
         // two-word states: split point of the decode / encode (see DevSpec::split_ok)
         sp.split_ok = 0;
         if (sp.words == 2 && n >= 2) {
@@ -428,7 +429,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         const int t = atoi(e);
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
     }
-    const bool luts = sp.divL.fix == 0 &&
+    // (the shared-memory kernels also estimate chunk quotients in fp64, which needs L**4 < 2**52 and L*L < 2**31)
+    const bool luts = sp.divL.fix == 0 && (u128)sp.LL * sp.LL < ((u128)1 << 52) && sp.LL < (1u << 31) &&
                       MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.backup_slab_bytes <= smem_limit;
     if (!luts) ctx->threads = 256;
     sp.lut_smem = luts ? 1 : 0;

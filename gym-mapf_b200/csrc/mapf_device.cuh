@@ -72,6 +72,7 @@ struct DevSpec {
     u64 nA;            // 5**n
     u64 smax[2];       // nS - 1
     FastDiv divLL;     // division by L*L
+    double invLL;      // 1 / (L*L)
     // Two-word states: s = q * D + r with D = L**KLO(n) splits the digits into a low and a high group that are then
     // decoded independently with one-word arithmetic (split_ok: D < 2**63 and L**(n - KLO) < 2**49, so that one fp64
     // estimate of q is off by at most one).  Otherwise: long division over 32-bit limbs.
@@ -131,8 +132,23 @@ __device__ __forceinline__ void decode_word(const DevSpec &sp, u64 x, int *cell)
 #pragma unroll
     for (int p = 0; p < PAIRS; ++p) {
         if (p + 1 < PAIRS) {
-            const u64 q = fastdiv(x, sp.divLL);
-            chunk[p] = (u32)x - (u32)q * sp.LL;
+            u64 q;
+            if (EXACT && N - 2 * p <= 4) {
+                // At most four digits left and (guaranteed with EXACT, i.e. whenever the move table is staged in shared
+                // memory: L <= 5632) L**4 < 2**52, L*L < 2**31: the quotient comes from the
+                // otherwise idle fp64 pipe.  2**52 + x is the double whose mantissa is x, so x -> double is one add;
+                // the product with 1/(L*L) is within 2**-20 of x / (L*L), so rounding it to the nearest integer (one
+                // more add of 2**52) gives floor or floor + 1, and the sign of the remainder tells which.
+                const double d = __dadd_rn(__hiloint2double(0x43300000 | (int)(u32)(x >> 32), (int)(u32)x), -4503599627370496.0);
+                u32 qq = (u32)__double2loint(__dadd_rn(__dmul_rn(d, sp.invLL), 4503599627370496.0));
+                int r = (int)((u32)x - qq * sp.LL);
+                if (r < 0) { r += (int)sp.LL; qq -= 1u; }
+                chunk[p] = (u32)r;
+                q = qq;
+            } else {
+                q = fastdiv(x, sp.divLL);
+                chunk[p] = (u32)x - (u32)q * sp.LL;
+            }
             x = q;
         } else {
             chunk[p] = (u32)x;
