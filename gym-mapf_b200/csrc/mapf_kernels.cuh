@@ -957,11 +957,25 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
     // this grid drains, and do our own prologue before waiting for the previous grid's results to be visible.
     asm volatile("griddepcontrol.launch_dependents;");
     SmemTables tb = tables_begin<LUTS>(sp, smem);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     bool ready = false;
     const u32 n_items = B / EPT;
     const u32 stride = gridDim.x * blockDim.x;
     u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    // The slip draws depend on nothing but (seed, env, step): those of the first item are generated BEFORE the wait
+    // on the previous grid (they overlap its tail and the first DRAM round trip), those of every later item at the
+    // end of the iteration before it.
+    constexpr int NW = ((N + 3) / 4) * 4;
+    u32 draws[EPT][NW];
+    if (!TAPE && it < n_items) {
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) {
+            EnvIn<N> tmp;
+            env_draws<N>(keys, env0 + (u64)(it * EPT + q), step, tmp);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) draws[q][j] = tmp.w[j];
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     RawIn<WORDS, EPT> raw;
     if (it < n_items) load_raw<WORDS, EPT>(states, actions, it, raw);
     while (it < n_items) {
@@ -971,6 +985,10 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         for (int q = 0; q < EPT; ++q) {
             in[q].lo = raw.lo[q];
             in[q].hi = raw.hi[q];
+            if (!TAPE) {
+#pragma unroll
+                for (int j = 0; j < NW; ++j) in[q].w[j] = draws[q][j];
+            }
         }
         const u32 a_raw[2] = {raw.a[0], raw.a[EPT - 1]};
         const u32 it_next = it + stride;
@@ -982,7 +1000,6 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
-            if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step, in[q]);
         }
         if (!ready) { tables_wait<LUTS>(smem); ready = true; }
         EnvOut o[EPT];
@@ -1012,6 +1029,15 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
             prob[b] = o[0].prob;
             done[b] = (u8)o[0].done;
             coll[b] = (u8)o[0].coll;
+        }
+        if (!TAPE && it_next < n_items) {
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) {
+                EnvIn<N> tmp;
+                env_draws<N>(keys, env0 + (u64)(it_next * EPT + q), step, tmp);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) draws[q][j] = tmp.w[j];
+            }
         }
         it = it_next;
     }
