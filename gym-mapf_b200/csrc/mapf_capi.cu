@@ -424,7 +424,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         mapf_ctx_destroy(ctx);
         return fail(MAPF_ERR_UNSUPPORTED, "no kernels for %d agents with %d-word states", n, sp.words);
     }
-    ctx->threads = lut_pad > 64 * 1024 ? 512 : 256;
+    ctx->threads = 512;  // two CTAs per SM stage the shared-memory image half as often as four of 256 (measured faster)
     if (const char *e = getenv("MAPF_THREADS")) {  // tuning experiments only
         const int t = atoi(e);
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;

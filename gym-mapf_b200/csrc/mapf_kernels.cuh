@@ -12,6 +12,9 @@
 #ifndef MAPF_ABLATE
 #define MAPF_ABLATE 0  // timing experiments only (tools/sweep8.sh); 0 = the real kernel
 #endif
+#ifndef MAPF_PREFETCH_ITEMS
+#define MAPF_PREFETCH_ITEMS 1
+#endif
 #ifndef MAPF_MAX_THREADS
 #define MAPF_MAX_THREADS 512  // largest CTA the hot kernels are launched with
 #endif
@@ -974,6 +977,12 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
 #pragma unroll
             for (int j = 0; j < NW; ++j) draws[q][j] = tmp.w[j];
         }
+    }
+    // pull this thread's input lines towards L2 while the previous grid drains (a prefetch cannot observe stale
+    // data: the loads below are issued after the wait); at most MAPF_PREFETCH_ITEMS grid-stride items ahead
+    for (u32 pf = it, k = 0; pf < n_items && k < MAPF_PREFETCH_ITEMS; pf += stride, ++k) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(states) + (size_t)pf * EPT * WORDS * 8));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + (size_t)pf * EPT));
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     RawIn<WORDS, EPT> raw;
