@@ -28,7 +28,7 @@ R_CLASH, R_GOAL, R_LIVING = -1000.0, 100.0, -1.0
 ENVS_PER_GPU = 1 << 20
 STEP_BYTES = 38           # 2W + 22 with W = 8
 RING_SLOTS = 32           # 32 x (12 MB in + 26 MB out) = 1.2 GB >> 126 MB L2
-NCU_DRAM_BYTES_PER_ENV = (100708864 + 163293440) / (1 << 23)   # profiles/r01_g_step_8m_raw.csv
+NCU_DRAM_BYTES_PER_ENV = (100711936 + 162370048) / (1 << 23)   # profiles/r01_h_step_8m_raw.csv
 METRIC = "joint transitions/sec"
 
 
@@ -364,9 +364,9 @@ def run_ours(args):
                                                              reps_sorted[-1]],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_ENV * B,
-                             "traffic_source": "ncu --set full, profiles/r01_g_step_8m_raw.csv: dram__bytes_read 100.7 MB "
-                                               "+ dram__bytes_write 163.3 MB for a 2**23-env launch = 31.5 B/env (reads = "
-                                               "the algorithmic 12 B/env; 19.5 of the 26 B/env written had reached DRAM "
+                             "traffic_source": "ncu --set full, profiles/r01_h_step_8m_raw.csv: dram__bytes_read 100.7 MB "
+                                               "+ dram__bytes_write 162.4 MB for a 2**23-env launch = 31.4 B/env (reads = "
+                                               "the algorithmic 12 B/env; 19.4 of the 26 B/env written had reached DRAM "
                                                "when the kernel ended, the rest was still in the 126 MB L2)",
                              "peak_source": peak_src,
                              "kernel": "k_step<4,smem move table>", "bytes_per_unit": STEP_BYTES,
