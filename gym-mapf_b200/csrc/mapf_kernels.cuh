@@ -1055,7 +1055,7 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
 
 // T steps per launch; the env's cells stay in registers between steps, each step's results go to slab t.
 template <int N, int WORDS, bool LUTS, bool TAPE>
-__global__ void __launch_bounds__(MAPF_MAX_THREADS)
+__global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
 k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ actions, i64 T, u32 B,
           const double *__restrict__ uniforms, u64 step0, u64 env0, u32 opts, u64 *__restrict__ next_states,
           double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
