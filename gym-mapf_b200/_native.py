@@ -151,6 +151,7 @@ class Engine:
         self.max_row_len = info.max_row_len
         self.sm_count = info.sm_count
         self._moves = None
+        self._mapf_step = lib().mapf_step  # hot call: skip the attribute lookups
 
     def close(self):
         if getattr(self, "_h", None):
@@ -166,7 +167,7 @@ class Engine:
     # ---- helpers
     def _stream(self):
         import torch
-        return torch.cuda.current_stream(self.torch_device).cuda_stream
+        return torch.cuda.current_stream(self.device_index).cuda_stream
 
     def state_shape(self, B):
         return (B,) if self.words == 1 else (B, 2)
@@ -270,17 +271,20 @@ class Engine:
 
     # ---- step / rollout
     def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None):
-        import torch
         B = states.shape[0]
-        dev = self.torch_device
         if out is None:
+            import torch
+            dev = self.torch_device
             out = (self.new_states(B), torch.empty(B, dtype=torch.float64, device=dev),
                    torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.bool, device=dev),
                    torch.empty(B, dtype=torch.bool, device=dev))
         ns, reward, prob, done, coll = out
-        check(lib().mapf_step(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
-                              OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
-                              _ptr(coll), self._stream()))
+        rc = self._mapf_step(self._h, states.data_ptr(), actions.data_ptr(), B,
+                             None if uniforms is None else uniforms.data_ptr(), seed, step_index, env_offset,
+                             OPT_AUTO_RESET if auto_reset else 0, ns.data_ptr(), reward.data_ptr(), prob.data_ptr(),
+                             done.data_ptr(), coll.data_ptr(), self._stream())
+        if rc:
+            check(rc)
         return out
 
     def rollout(self, states, actions, T, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=True, out=None):

@@ -15,10 +15,12 @@ Rollout = collections.namedtuple("Rollout", "next_state reward prob done collisi
 
 
 class VecMapfEnv:
-    def __init__(self, env, num_envs, device=None, seed=0, auto_reset=True):
+    def __init__(self, env, num_envs, device=None, seed=0, auto_reset=True, reuse_outputs=False):
         """`env`: a MapfEnv (its spec and device context are shared).  `seed` keys the Philox sampling stream;
         `auto_reset`: an env whose step returns done restarts from the start state (its returned next state is then
-        the start state, as in gym's vector envs)."""
+        the start state, as in gym's vector envs).  `reuse_outputs`: `step()` alternates between two preallocated
+        sets of result tensors instead of allocating five new ones per call (the tensors returned by a step are
+        overwritten two steps later); with it a `step()` costs ~9 us of host time instead of ~20."""
         import torch
         self.env = env
         if device is not None and env._engine_obj is None:
@@ -33,6 +35,13 @@ class VecMapfEnv:
         self.n_agents, self.nS, self.nA = env.n_agents, env.nS, env.nA
         self.states = self.engine.new_states(self.num_envs)
         self._torch = torch
+        self._ring = None
+        if reuse_outputs:
+            B, dev = self.num_envs, self.device
+            self._ring = [(self.engine.new_states(B), torch.empty(B, dtype=torch.float64, device=dev),
+                           torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.bool, device=dev),
+                           torch.empty(B, dtype=torch.bool, device=dev)) for _ in range(2)]
+            self.states = self._ring[1][0]
         self.reset()
 
     # ---- encodings ---------------------------------------------------------------------------------------------
@@ -65,9 +74,10 @@ class VecMapfEnv:
         """One joint step of every env.  Returns (next_states, rewards, dones, info) with
         info = {"prob": f64[B], "collision": bool[B]}.  `uniforms` (f64[B, n]) replays given draws bit-exactly;
         without it the device-side Philox stream keyed by (seed, env, step) is used."""
+        out = None if self._ring is None else self._ring[self.step_count & 1]
         ns, reward, prob, done, coll = self.engine.step(
             self.states, actions, uniforms=uniforms, seed=self.seed, step_index=self.step_count,
-            env_offset=self.env_offset, auto_reset=self.auto_reset)
+            env_offset=self.env_offset, auto_reset=self.auto_reset, out=out)
         self.states = ns
         self.step_count += 1
         return ns, reward, done, {"prob": prob, "collision": coll}
