@@ -566,3 +566,112 @@ def test_thirteen_agents(torch):
     glo, ghi = split_states(eng, ns)
     assert np.array_equal(glo, ws["next_lo"]) and np.array_equal(ghi, ws["next_hi"])
     assert np.array_equal(u64(prob), G.f64_to_bits(ws["prob"])) and np.array_equal(u64(reward), G.f64_to_bits(ws["reward"]))
+
+
+def _random_spec(rng):
+    H, W = int(rng.integers(1, 8)), int(rng.integers(1, 8))
+    while True:
+        grid = rng.random((H, W)) < rng.choice([0.0, 0.15, 0.4])
+        if (~grid).sum() >= 1:
+            break
+    free = [(r, c) for r in range(H) for c in range(W) if not grid[r, c]]
+    n = int(rng.integers(1, 6))
+    pick = lambda: [list(free[int(rng.integers(0, len(free)))]) for _ in range(n)]  # noqa: E731
+    fp = float(rng.choice([0.0, 0.1, 0.2, 0.37, 0.5, 1.0]))
+    return dict(rows=["".join("@" if v else "." for v in row) for row in grid], n_agents=n, starts=pick(), goals=pick(),
+                fail_prob=fp, r_clash=float(rng.choice([-1000.0, -3.5, 0.0])), r_goal=float(rng.choice([100.0, 7.25, 1.0])),
+                r_living=float(rng.choice([-1.0, -0.25, 0.0])), soc=bool(rng.integers(0, 2)))
+
+
+def test_fuzz_random_specs(torch):
+    """Differential test on 80 random env specs (tiny grids down to a single free cell, 1-5 agents, every noise level
+    including 0 and 1, both criteria, starts/goals that may coincide): rows, steps with given uniforms, the fused
+    backup, predecessors and projections must equal the C oracle bit for bit."""
+    rng = np.random.default_rng(2026)
+    for case in range(80):
+        spec = _random_spec(rng)
+        eng = make_engine(spec)
+        ora = make_oracle(spec)
+        nS, nA = eng.nS, eng.nA
+        B = int(min(4000, nS * nA))
+        if nS * nA <= 4000:
+            s = np.repeat(np.arange(nS, dtype=np.uint64), nA)
+            a = np.tile(np.arange(nA, dtype=np.int64), nS)
+        else:
+            s = rng.integers(0, nS, B).astype(np.uint64)
+            a = rng.integers(0, nA, B).astype(np.int64)
+        z = np.zeros_like(s)
+        st = states_tensor(eng, s, z)
+        at = torch.from_numpy(a.astype(np.int32)).to(eng.torch_device)
+        want = ora.rows(s, z, a)
+        got = eng.transitions(st, at)
+        assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                          G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+        uni = rng.random((len(s), eng.n))
+        ws = ora.step(s, z, a, uni)
+        ns, reward, prob, done, coll = eng.step(st, at, uniforms=torch.from_numpy(uni).to(eng.torch_device))
+        assert np.array_equal(u64(ns), ws["next_lo"]), (case, spec)
+        assert np.array_equal(u64(reward), G.f64_to_bits(ws["reward"])) and np.array_equal(u64(prob), G.f64_to_bits(ws["prob"]))
+        assert np.array_equal(done.cpu().numpy().astype(np.uint8), ws["done"])
+        assert np.array_equal(coll.cpu().numpy().astype(np.uint8), ws["collision"])
+        V = rng.normal(0, 20, nS)
+        q = eng.backup(st, at, torch.from_numpy(V).to(eng.torch_device), 0.9)
+        assert np.array_equal(u64(q), G.f64_to_bits(ora.backup(s, z, a, V, 0.9))), (case, spec)
+        wp = ora.predecessors(s[:200], z[:200])
+        row_ptr, pred = eng.predecessors(st[:200])
+        assert np.array_equal(row_ptr.cpu().numpy(), wp["row_ptr"])
+        plo = u64(pred)
+        for b in range(min(200, len(s))):
+            sl = slice(int(wp["row_ptr"][b]), int(wp["row_ptr"][b + 1]))
+            assert np.array_equal(np.sort(plo[sl]), wp["pred_lo"][sl])
+        sub = [int(x) for x in rng.permutation(eng.n)[:int(rng.integers(1, eng.n + 1))]]
+        assert np.array_equal(u64(eng.project(st, sub)), ora.project(s, z, sub)[0])
+        # the device-side sampling mode needs slip probabilities that add up to 1 (always true here)
+        eng.step(st, at, seed=case)
+        eng.close()
+
+
+def test_fuzz_two_word_specs(torch):
+    """The same differential test where the joint state needs two words (10-13 agents on 40-64 free cells): both the
+    split decode/encode (L**k groups) and the limb long division are exercised, depending on L and n."""
+    rng = np.random.default_rng(77)
+    seen_split = set()
+    for case in range(10):
+        H, W = int(rng.integers(6, 9)), int(rng.integers(7, 9))
+        grid = rng.random((H, W)) < 0.1
+        free = [(r, c) for r in range(H) for c in range(W) if not grid[r, c]]
+        n = int(rng.integers(10, 14))
+        if len(free) ** n < 2 ** 63:
+            continue
+        pick = lambda: [list(free[int(rng.integers(0, len(free)))]) for _ in range(n)]  # noqa: E731
+        spec = dict(rows=["".join("@" if v else "." for v in row) for row in grid], n_agents=n, starts=pick(), goals=pick(),
+                    fail_prob=float(rng.choice([0.2, 0.5])), r_clash=-1000.0, r_goal=100.0, r_living=-1.0,
+                    soc=bool(rng.integers(0, 2)))
+        eng = make_engine(spec)
+        assert eng.words == 2
+        ora = make_oracle(spec)
+        B = 3000
+        cells = rng.integers(0, eng.L, (B, n)).astype(np.int32)
+        cells[::3] = np.stack([rng.permutation(eng.L)[:n] for _ in range(len(cells[::3]))])  # no duplicates: not terminal
+        lo, hi = ora.encode(cells)
+        st = states_tensor(eng, lo, hi)
+        a = rng.integers(0, eng.nA, B).astype(np.int64)
+        at = torch.from_numpy(a.astype(np.int32)).to(eng.torch_device)
+        # decode / encode round trip and steps on the whole batch
+        assert np.array_equal(eng.decode(st).cpu().numpy(), cells)
+        uni = rng.random((B, n))
+        ws = ora.step(lo, hi, a, uni)
+        ns, reward, prob, done, coll = eng.step(st, at, uniforms=torch.from_numpy(uni).to(eng.torch_device))
+        glo, ghi = split_states(eng, ns)
+        assert np.array_equal(glo, ws["next_lo"]) and np.array_equal(ghi, ws["next_hi"]), (case, eng.L, n)
+        assert np.array_equal(u64(prob), G.f64_to_bits(ws["prob"])) and np.array_equal(u64(reward), G.f64_to_bits(ws["reward"]))
+        # a few rows (each up to 3**n records): mostly-STAY actions keep them small
+        digits = (rng.random((6, n)) < 0.35) * rng.integers(1, 5, (6, n))
+        ar = (digits * (5 ** np.arange(n))).sum(axis=1).astype(np.int64)
+        want = ora.rows(lo[:6], hi[:6], ar)
+        got = eng.transitions(st[:6], torch.from_numpy(ar.astype(np.int32)).to(eng.torch_device))
+        assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                          G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+        seen_split.add((eng.L, n))
+        eng.close()
+    assert len(seen_split) >= 4
