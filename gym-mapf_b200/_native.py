@@ -165,6 +165,22 @@ class Engine:
             pass
 
     # ---- helpers
+    def _check_batch(self, states, actions, uniforms=None):
+        """Cheap host-side validation of a (states, actions[, uniforms]) batch: wrong dtypes, shapes or devices would
+        otherwise be read as garbage by the kernels.  (Value ranges are not checked here -- that would need a device
+        synchronisation; the kernels clamp out-of-range states and actions instead of faulting.)"""
+        import torch
+        B = states.shape[0]
+        if states.dtype is not torch.int64 or tuple(states.shape) != self.state_shape(B) or not states.is_contiguous():
+            raise ValueError("states must be a contiguous int64 tensor of shape %s" % (self.state_shape(B),))
+        if actions.dtype is not torch.int32 or tuple(actions.shape) != (B,) or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous int32 tensor of shape (%d,)" % B)
+        if states.device != self.torch_device or actions.device != self.torch_device:
+            raise ValueError("states and actions must live on %s" % self.torch_device)
+        if uniforms is not None and (uniforms.dtype is not torch.float64 or tuple(uniforms.shape) != (B, self.n)
+                                     or not uniforms.is_contiguous() or uniforms.device != self.torch_device):
+            raise ValueError("uniforms must be a contiguous float64 tensor of shape (%d, %d) on %s" % (B, self.n, self.torch_device))
+
     def _stream(self):
         import torch
         return torch.cuda.current_stream(self.device_index).cuda_stream
@@ -238,6 +254,7 @@ class Engine:
         """CSR expansion of P[states[b]][actions[b]] -> (row_ptr, next_state, prob, reward, flags), all on device."""
         import torch
         B = states.shape[0]
+        self._check_batch(states, actions)
         row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
         check(lib().mapf_count_rows(self._h, _ptr(states), _ptr(actions), B, _ptr(row_len), self._stream()))
         row_ptr = self._scan(row_len)
@@ -272,6 +289,7 @@ class Engine:
     # ---- step / rollout
     def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None):
         B = states.shape[0]
+        self._check_batch(states, actions, uniforms)
         if out is None:
             import torch
             dev = self.torch_device

@@ -675,3 +675,20 @@ def test_fuzz_two_word_specs(torch):
         seen_split.add((eng.L, n))
         eng.close()
     assert len(seen_split) >= 4
+
+
+def test_batch_validation(torch):
+    spec, _ = G.load("rows_c2")
+    eng = make_engine(spec)
+    st = eng.states_from_ints([eng.s0] * 8)
+    good = torch.zeros(8, dtype=torch.int32, device=eng.torch_device)
+    eng.step(st, good)
+    for bad in (good.to(torch.int64), good[:7], good.cpu(), torch.zeros(16, dtype=torch.int32, device=eng.torch_device)[::2]):
+        with pytest.raises(ValueError):
+            eng.step(st, bad)
+        with pytest.raises(ValueError):
+            eng.transitions(st, bad)
+    with pytest.raises(ValueError):
+        eng.step(st.to(torch.int32), good)
+    with pytest.raises(ValueError):
+        eng.step(st, good, uniforms=torch.zeros(8, 3, dtype=torch.float64, device=eng.torch_device))

@@ -108,9 +108,14 @@ def c2_expand():
 
 def c5_sweep():
     rng = np.random.default_rng(5)
+    only = [int(x) for x in os.environ.get("PERF_N", "").split(",") if x]
     for n in range(2, 11):
+        if only and n not in only:
+            continue
         expand_case("c5_expand empty-32-32 n=%d" % n, make("empty-32-32", 1, n), 1 << 16, rng)
     for w in (16, 8, 4, 2):
+        if only and 6 not in only:
+            continue
         expand_case("c5_density empty-32-32 n=6 window=%d" % w, make("empty-32-32", 1, 6), 1 << 16, rng, window=w)
 
 
