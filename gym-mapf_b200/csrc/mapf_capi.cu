@@ -275,6 +275,16 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         sp.LL = (u32)ll;
         sp.divLL = make_fastdiv(ll);
         sp.invLL = 1.0 / (double)ll;
+        // expand with cached head agents (see HeadCache): tail = last six agents
+        sp.head_ok = 0;
+        sp.powLH = 1;
+        if (n >= EXPAND_HEAD_MIN_AGENTS) {
+            u128 t6 = 1, th = 1;
+            for (int i = 0; i < EXPAND_TAIL_AGENTS; ++i) t6 *= (u128)L;
+            bool fits = t6 < ((u128)1 << 63);
+            for (int i = 0; i < n - EXPAND_TAIL_AGENTS; ++i) { th *= (u128)L; fits = fits && th < ((u128)1 << 63); }
+            if (fits) { sp.head_ok = 1; sp.powLH = (u64)th; }
+        }
         // two-word states: split point of the decode / encode (see DevSpec::split_ok)
         sp.split_ok = 0;
         if (sp.words == 2 && n >= 2) {

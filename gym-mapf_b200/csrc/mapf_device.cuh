@@ -77,7 +77,8 @@ struct DevSpec {
     // decoded independently with one-word arithmetic (split_ok: D < 2**63 and L**(n - KLO) < 2**49, so that one fp64
     // estimate of q is off by at most one).  Otherwise: long division over 32-bit limbs.
     int split_ok;
-    int pad2;
+    int head_ok;       // expand: the tail agents and the agents before them each fit one word (see HeadCache)
+    u64 powLH;         // L**(number of head agents)
     u64 splitD;
     double invD;
     Div32 divL;        // division by L of a two-digit chunk

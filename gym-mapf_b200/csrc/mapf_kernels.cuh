@@ -309,6 +309,9 @@ static __constant__ u64 RECIP_POW3[14] = {
     17355401703772ull,      5785133901257ull};
 
 #define EXPAND_MAX_PAIRS 4
+// chunks per warp: many agents -> rows of very different cost per record exist (pair-list overflow), spread them
+#define EXPAND_CHUNKS_PER_WARP(n) ((n) >= 8 ? 4 : 1)
+#define EXPAND_CHUNK_MIN 1024
 #ifndef EXPAND_LIST_MIN_AGENTS
 #define EXPAND_LIST_MIN_AGENTS 8
 #endif
@@ -485,6 +488,94 @@ __device__ __forceinline__ RecordOut expand_record(const DevSpec &sp, const Smem
     return out;
 }
 
+// From EXPAND_HEAD_MIN_AGENTS agents on, a lane caches what the first H = N - 6 agents ("head": the slowest digits of
+// the product order) contribute to a record: the prefix of the probability product, their part of the next-state
+// index and their digits.  The lane's records are 32 apart, the head digits change only every prod(k_i, i >= H)
+// records (up to 729), so almost every record is evaluated from its six tail agents alone.
+#ifndef EXPAND_HEAD_MIN_AGENTS
+#define EXPAND_HEAD_MIN_AGENTS 9
+#endif
+#ifndef EXPAND_TAIL_AGENTS
+#define EXPAND_TAIL_AGENTS 6
+#endif
+struct HeadCache {
+    int row;      // slab row the cached values belong to (-1: none)
+    u32 dvh;      // the head digits, two bits per agent
+    double p;     // ((p_0 * p_1) * ...) * p_{H-1}
+    u64 hpart;    // sum of dest_i * L**i over the head
+};
+
+template <int N, int WORDS>
+__device__ __forceinline__ RecordOut expand_record_cached(const DevSpec &sp, const SmemTables &tb, const ExpandSlab<N> &sl,
+                                                          int row, u32 flag, u32 o, HeadCache &hc) {
+    constexpr int H = N - EXPAND_TAIL_AGENTS, T = EXPAND_TAIL_AGENTS;
+    RecordOut out;
+    u32 x = (u32)(((u64)(2u * o + 1u) * sl.rcp[row]) >> 32);
+    u32 hd[H], dvh = 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {  // the head digits (agent 0 slowest)
+        const u64 wide = (u64)x * (u64)((u32)(sl.ent[i][row] >> 56));
+        hd[i] = (u32)(wide >> 32);
+        x = (u32)wide;
+        dvh += hd[i] << (2 * i);
+    }
+    if (hc.row != row || hc.dvh != dvh) {  // a new head combination: rare
+        int hcell[H];
+        double p = 0.0;
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            const u64 e = sl.ent[i][row];
+            hcell[i] = (int)ent_dest(e, hd[i]);
+            const double pi = lds_f64<MAPF_SMEM_PP>(tb.base + ENT_POFF(e) + hd[i] * 8u);
+            p = i == 0 ? pi : __dmul_rn(p, pi);
+        }
+        hc.row = row;
+        hc.dvh = dvh;
+        hc.p = p;
+        hc.hpart = encode_word<H>(sp, hcell);
+    }
+    int tcell[T];
+    double p = hc.p;
+    u32 dv = dvh;
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+        const u64 e = sl.ent[H + i][row];
+        const u64 wide = (u64)x * (u64)((u32)(e >> 56));
+        const u32 d = (u32)(wide >> 32);
+        x = (u32)wide;
+        tcell[i] = (int)ent_dest(e, d);
+        p = __dmul_rn(p, lds_f64<MAPF_SMEM_PP>(tb.base + ENT_POFF(e) + d * 8u));  // left to right (mapf_env.py:468)
+        dv += d << (2 * (H + i));
+    }
+    bool clash = false;
+    for (u32 q = 0; q < (flag >> 1); ++q) {
+        const u32 desc = sl.pair[q][row];
+        const u32 di = (dv >> (desc & 31u)) & 3u, dj = (dv >> ((desc >> 5) & 31u)) & 3u;
+        clash = clash || ((desc >> (10u + 3u * di + dj)) & 1u);
+    }
+    // next state = tail * L**H + head
+    const u64 tpart = encode_word<T>(sp, tcell);
+    const u64 plo = tpart * sp.powLH;
+    out.lo = plo + hc.hpart;
+    out.hi = WORDS == 2 ? __umul64hi(tpart, sp.powLH) + (out.lo < plo ? 1ull : 0ull) : 0ull;
+    const bool goal = out.lo == sp.sgoal[0] && out.hi == sp.sgoal[1];
+    const int kind = clash ? 1 : (goal ? 2 : 0);
+    out.p = p;
+    out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + (u32)(kind * MAPF_REW_STRIDE + sl.parked[row]) * 8u);
+    out.flags = (kind != 0 ? 1u : 0u) | (clash ? 2u : 0u);
+    return out;
+}
+
+// dispatch: the cached evaluation needs the pair list (not the all-pairs fallback) and one-word head / tail parts
+template <int N, int WORDS>
+__device__ __forceinline__ RecordOut expand_record_any(const DevSpec &sp, const SmemTables &tb, const ExpandSlab<N> &sl,
+                                                       int row, u32 flag, u32 o, HeadCache &hc) {
+    if constexpr (N >= EXPAND_HEAD_MIN_AGENTS) {
+        if (sp.head_ok && !(flag & 16u)) return expand_record_cached<N, WORDS>(sp, tb, sl, row, flag, o, hc);
+    }
+    return expand_record<N, WORDS>(sp, tb, sl, row, flag, o);
+}
+
 template <int N, int WORDS, bool LUTS, bool RANGE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS)
 k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
@@ -498,76 +589,87 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
     const i64 M = row_ptr[B];
     const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
-    const i64 chunk = ((M + 32 * n_warps - 1) / (32 * n_warps)) * 32;  // records per warp, a multiple of 32
-    const i64 lo = ((i64)blockIdx.x * (blockDim.x >> 5) + wid) * chunk;
-    const i64 hi = lo + chunk < M ? lo + chunk : M;
+    // Records are dealt out in chunks of consecutive records, chunk c to warp c mod n_warps, EXPAND_CHUNKS_PER_WARP(N)
+    // chunks per warp (at least EXPAND_CHUNK_MIN records each, a multiple of 32): a row whose records are expensive
+    // (more conflicting pairs than the list holds) or a giant row is spread over several warps instead of making
+    // one warp the straggler of the launch, at the price of one row search per chunk.
+    i64 per = (M + n_warps * EXPAND_CHUNKS_PER_WARP(N) - 1) / (n_warps * EXPAND_CHUNKS_PER_WARP(N));
+    per = ((per < EXPAND_CHUNK_MIN ? EXPAND_CHUNK_MIN : per) + 31) & ~31ll;
+    const i64 n_chunks = (M + per - 1) / per;
     tables_wait<LUTS>(smem);
-    if (lo >= hi) return;
-    // ---------------- 0: the row r with row_ptr[r] <= lo < row_ptr[r + 1]
-    i64 r;
-    {
-        i64 a = 0, b = B;  // row_ptr[a] <= lo < row_ptr[b]
-        while (b - a > 1) {
-            const i64 step = (b - a + 31) >> 5;
-            i64 p = a + (i64)(lane + 1) * step;
-            p = p < b ? p : b;
-            const int c = __popc(__ballot_sync(FULL, row_ptr[p] <= lo));  // probes are increasing: a prefix is true
-            const i64 nb = a + (i64)(c + 1) * step;
-            a += (i64)c * step;
-            b = nb < b ? nb : b;
-        }
-        r = a;
-    }
-    for (;;) {
-        // ---------------- phase A: rows r .. r + 31 (those that start before `hi`)
-        const i64 b = r + lane;
-        const i64 start = b < B ? row_ptr[b] : M;
-        const i64 batch_begin = __shfl_sync(FULL, start, 0);
-        const bool need = b < B && start < hi;
-        const u32 len = need ? expand_row_setup<N, WORDS, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, sb_hi, b) : 0u;
-        u32 incl = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 y = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += y;
-        }
-        const u32 total = __shfl_sync(FULL, incl, 31);
-        const int myrel = (int)(incl - len);  // first record of my row, relative to batch_begin
-        sl.pref[lane] = (u32)myrel;
-        __syncwarp();
-        // ---------------- phase B: records [first, last) of this batch, in 32-aligned windows
-        const i64 batch_end = batch_begin + total;
-        const i64 first = lo > batch_begin ? lo : batch_begin;
-        const i64 last = hi < batch_end ? hi : batch_end;
-        const int first_rel = (int)(first - batch_begin), last_rel = (int)(last - batch_begin);
-        i64 w = first & ~31ll;
-        int wrel = (int)(w - batch_begin);  // may be negative in a batch's first window
-        int rows_before = __popc(__ballot_sync(FULL, need && myrel < wrel));  // rows starting before the window
-        for (; wrel < last_rel; wrel += 32, w += 32) {
-            const bool inwin = need && myrel >= wrel && myrel < wrel + 32;
-            const u32 heads = __reduce_or_sync(FULL, inwin ? 1u << (myrel - wrel) : 0u);
-            const int row = rows_before + __popc(heads & lane_le) - 1;
-            rows_before += __popc(heads);
-            const int rel = wrel + lane;
-            if (rel < first_rel || rel >= last_rel) continue;
-            const i64 idx = w + lane;
-            const u32 flag = sl.flag[row];
-            if (flag & 1u) {  // [((1.0, False), s, 0, True)]  (mapf_env.py:455-456)
-                store_state<WORDS>(next_state, idx, sl.st[0][row], sl.st[1][row]);
-                prob[idx] = 1.0;
-                reward[idx] = 0.0;
-                flags[idx] = 1;
-                continue;
+    HeadCache hc;
+    constexpr bool MULTI = EXPAND_CHUNKS_PER_WARP(N) > 1;
+    for (i64 chunk = (i64)blockIdx.x * (blockDim.x >> 5) + wid; chunk < n_chunks; chunk += n_warps) {
+        const i64 lo = chunk * per;
+        const i64 hi = lo + per < M ? lo + per : M;
+        // ---------------- 0: the row r with row_ptr[r] <= lo < row_ptr[r + 1]
+        i64 r;
+        {
+            i64 a = 0, b = B;  // row_ptr[a] <= lo < row_ptr[b]
+            while (b - a > 1) {
+                const i64 step = (b - a + 31) >> 5;
+                i64 p = a + (i64)(lane + 1) * step;
+                p = p < b ? p : b;
+                const int c = __popc(__ballot_sync(FULL, row_ptr[p] <= lo));  // probes are increasing: a prefix is true
+                const i64 nb = a + (i64)(c + 1) * step;
+                a += (i64)c * step;
+                b = nb < b ? nb : b;
             }
-            const RecordOut rec = expand_record<N, WORDS>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row]);
-            store_state<WORDS>(next_state, idx, rec.lo, rec.hi);
-            prob[idx] = rec.p;
-            reward[idx] = rec.reward;
-            flags[idx] = (u8)rec.flags;
+            r = a;
         }
-        if (batch_end >= hi || r + 32 >= B) break;
-        r += 32;
-        __syncwarp();
+        for (;;) {
+            __syncwarp();
+            hc.row = -1;  // the slab is about to be rewritten
+            // ---------------- phase A: rows r .. r + 31 (those that start before `hi`)
+            const i64 b = r + lane;
+            const i64 start = b < B ? row_ptr[b] : M;
+            const i64 batch_begin = __shfl_sync(FULL, start, 0);
+            const bool need = b < B && start < hi;
+            const u32 len = need ? expand_row_setup<N, WORDS, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, sb_hi, b) : 0u;
+            u32 incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const u32 total = __shfl_sync(FULL, incl, 31);
+            const int myrel = (int)(incl - len);  // first record of my row, relative to batch_begin
+            sl.pref[lane] = (u32)myrel;
+            __syncwarp();
+            // ---------------- phase B: records [first, last) of this batch, in 32-aligned windows
+            const i64 batch_end = batch_begin + total;
+            const i64 first = lo > batch_begin ? lo : batch_begin;
+            const i64 last = hi < batch_end ? hi : batch_end;
+            const int first_rel = (int)(first - batch_begin), last_rel = (int)(last - batch_begin);
+            i64 w = first & ~31ll;
+            int wrel = (int)(w - batch_begin);  // may be negative in a batch's first window
+            int rows_before = __popc(__ballot_sync(FULL, need && myrel < wrel));  // rows starting before the window
+            for (; wrel < last_rel; wrel += 32, w += 32) {
+                const bool inwin = need && myrel >= wrel && myrel < wrel + 32;
+                const u32 heads = __reduce_or_sync(FULL, inwin ? 1u << (myrel - wrel) : 0u);
+                const int row = rows_before + __popc(heads & lane_le) - 1;
+                rows_before += __popc(heads);
+                const int rel = wrel + lane;
+                if (rel < first_rel || rel >= last_rel) continue;
+                const i64 idx = w + lane;
+                const u32 flag = sl.flag[row];
+                if (flag & 1u) {  // [((1.0, False), s, 0, True)]  (mapf_env.py:455-456)
+                    store_state<WORDS>(next_state, idx, sl.st[0][row], sl.st[1][row]);
+                    prob[idx] = 1.0;
+                    reward[idx] = 0.0;
+                    flags[idx] = 1;
+                    continue;
+                }
+                const RecordOut rec = expand_record_any<N, WORDS>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row], hc);
+                store_state<WORDS>(next_state, idx, rec.lo, rec.hi);
+                prob[idx] = rec.p;
+                reward[idx] = rec.reward;
+                flags[idx] = (u8)rec.flags;
+            }
+            if (batch_end >= hi || r + 32 >= B) break;
+            r += 32;
+        }
+        if (!MULTI) break;  // one chunk per warp: no outer loop for the compiler to carry state around
     }
 }
 
@@ -605,6 +707,8 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     for (i64 batch = (i64)blockIdx.x * (blockDim.x >> 5) + wid; batch < n_batches; batch += n_warps) {
         const i64 b = batch * 32 + lane;
         const bool need = b < B;
+        HeadCache hc;
+        hc.row = -1;
         const u32 len = need ? expand_row_setup<N, 1, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, 0ull, b) : 0u;
         u32 incl = len;
 #pragma unroll
@@ -630,7 +734,7 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
                 if (flag & 1u) {  // the single record of a terminal state: (1.0, s, 0, True)
                     term = __dmul_rn(1.0, __dadd_rn(0.0, __dmul_rn(gamma, __ldg(V + sl.st[0][row]))));
                 } else {
-                    const RecordOut rec = expand_record<N, 1>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row]);
+                    const RecordOut rec = expand_record_any<N, 1>(sp, tb, sl, row, flag, (u32)rel - sl.pref[row], hc);
                     term = __dmul_rn(rec.p, __dadd_rn(rec.reward, __dmul_rn(gamma, __ldg(V + rec.lo))));
                 }
                 bs.term[lane] = term;
