@@ -17,7 +17,8 @@ OPT_AUTO_RESET = 1
 FLAG_DONE, FLAG_COLLISION = 1, 2
 
 EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
-           "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_expand",
+           "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_count_scan_rows",
+           "mapf_count_scan_range", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_rollout", "mapf_step_host",
            "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_greedy_bcast", "mapf_count_predecessors", "mapf_predecessors",
            "mapf_projected_words", "mapf_project_states", "mapf_last_error", "mapf_version"]
@@ -80,6 +81,8 @@ def lib():
         L.mapf_scan_scratch_bytes.argtypes = [i64]
         L.mapf_scan_scratch_bytes.restype = i64
         L.mapf_scan_rows.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mapf_count_scan_rows.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+        L.mapf_count_scan_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, vp, vp, vp]
         L.mapf_expand.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.mapf_count_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, vp]
         L.mapf_expand_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, vp, vp, vp, vp, vp]
@@ -244,6 +247,12 @@ class Engine:
         check(lib().mapf_scan_rows(self._h, _ptr(row_len), B, _ptr(row_ptr), _ptr(scratch), self._stream()))
         return row_ptr
 
+    def _scan_buffers(self, B):
+        import torch
+        row_ptr = torch.empty(B + 1, dtype=torch.int64, device=self.torch_device)
+        scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device=self.torch_device)
+        return row_ptr, scratch
+
     def _alloc_records(self, total):
         import torch
         dev = self.torch_device
@@ -256,8 +265,9 @@ class Engine:
         B = states.shape[0]
         self._check_batch(states, actions)
         row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
-        check(lib().mapf_count_rows(self._h, _ptr(states), _ptr(actions), B, _ptr(row_len), self._stream()))
-        row_ptr = self._scan(row_len)
+        row_ptr, scratch = self._scan_buffers(B)
+        check(lib().mapf_count_scan_rows(self._h, _ptr(states), _ptr(actions), B, _ptr(row_len), _ptr(row_ptr),
+                                         _ptr(scratch), self._stream()))
         total = int(row_ptr[-1].item())
         ns, prob, reward, flags = self._alloc_records(total)
         check(lib().mapf_expand(self._h, _ptr(states), _ptr(actions), B, _ptr(row_ptr), _ptr(ns), _ptr(prob),
@@ -270,8 +280,9 @@ class Engine:
         sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
         B = n_states * self.nA
         row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
-        check(lib().mapf_count_range(self._h, C.byref(sb), n_states, _ptr(row_len), self._stream()))
-        row_ptr = self._scan(row_len)
+        row_ptr, scratch = self._scan_buffers(B)
+        check(lib().mapf_count_scan_range(self._h, C.byref(sb), n_states, _ptr(row_len), _ptr(row_ptr), _ptr(scratch),
+                                          self._stream()))
         total = int(row_ptr[-1].item())
         ns, prob, reward, flags = self._alloc_records(total)
         check(lib().mapf_expand_range(self._h, C.byref(sb), n_states, _ptr(row_ptr), _ptr(ns), _ptr(prob), _ptr(reward),

@@ -611,6 +611,43 @@ extern "C" int mapf_count_range(const mapf_ctx *ctx, const uint64_t s_begin[2], 
     return count_impl(ctx, true, nullptr, nullptr, s_begin[0], s_begin[1], B, row_len, stream);
 }
 
+// count + scan in three launches instead of four (see k_count_partials)
+static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, const int32_t *actions, u64 sb_lo, u64 sb_hi,
+                           int64_t B, int64_t *row_len, int64_t *row_ptr, void *scratch, void *stream) {
+    if (!row_ptr || (B > 0 && (!row_len || !scratch))) return fail(MAPF_ERR_INVALID, "count_scan: NULL buffer");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0) {
+        CUDA_TRY(cudaMemsetAsync(row_ptr, 0, sizeof(int64_t), st));
+        return MAPF_OK;
+    }
+    const int64_t chunks = (B + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (chunks > 0x7fffffff) return fail(MAPF_ERR_INVALID, "too many rows for one scan");
+    DevSpec sp = ctx->sp;
+    i64 *partial = (i64 *)scratch;
+    void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
+    LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
+    k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+    k_scan_final<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr);
+    CUDA_TRY(cudaGetLastError());
+    return MAPF_OK;
+}
+
+extern "C" int mapf_count_scan_rows(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B,
+                                    int64_t *row_len, int64_t *row_ptr, void *scratch, void *stream) {
+    if (!ctx || B < 0 || (B > 0 && (!states || !actions))) return fail(MAPF_ERR_INVALID, "mapf_count_scan_rows: bad argument");
+    return count_scan_impl(ctx, false, states, actions, 0, 0, B, row_len, row_ptr, scratch, stream);
+}
+
+extern "C" int mapf_count_scan_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_states, int64_t *row_len,
+                                     int64_t *row_ptr, void *scratch, void *stream) {
+    if (!ctx || !s_begin) return fail(MAPF_ERR_INVALID, "mapf_count_scan_range: bad argument");
+    int64_t B = 0;
+    int rc = range_rows(ctx, n_states, &B);
+    if (rc) return rc;
+    return count_scan_impl(ctx, true, nullptr, nullptr, s_begin[0], s_begin[1], B, row_len, row_ptr, scratch, stream);
+}
+
 extern "C" int64_t mapf_scan_scratch_bytes(int64_t B) {
     int64_t chunks = (B + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (chunks < 1) chunks = 1;

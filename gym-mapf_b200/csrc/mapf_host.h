@@ -10,6 +10,7 @@ struct KernelSet {
     const void *rollout_philox = nullptr, *rollout_tape = nullptr;
     const void *expand = nullptr, *expand_range = nullptr;
     const void *count = nullptr, *count_range = nullptr;
+    const void *count_partials = nullptr, *count_partials_range = nullptr;  // row lengths + the scan's chunk sums
     const void *decode = nullptr, *encode = nullptr;
     const void *backup = nullptr, *backup_range = nullptr;  // k_backup<N, LUTS, RANGE>; one-word states only
     const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;

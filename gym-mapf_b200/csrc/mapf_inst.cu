@@ -18,6 +18,8 @@ static void fill(KernelSet *k) {
     k->expand_range = (const void *)k_expand<N, W, LUTS, true>;
     k->count = (const void *)k_count<N, W, false>;
     k->count_range = (const void *)k_count<N, W, true>;
+    k->count_partials = (const void *)k_count_partials<N, W, false>;
+    k->count_partials_range = (const void *)k_count_partials<N, W, true>;
     k->decode = (const void *)k_decode<N, W>;
     k->encode = (const void *)k_encode<N, W>;
     if (W == 1) {

@@ -289,6 +289,39 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) row_ptr[B] = partial[gridDim.x];
 }
 
+// Row lengths AND the per-chunk sums of the scan in one pass (saves the scan's first read of row_len and a launch):
+// block b owns rows [b * SCAN_CHUNK, (b + 1) * SCAN_CHUNK).
+template <int N, int WORDS, bool RANGE>
+__global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *__restrict__ states,
+                                                        const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
+                                                        i64 *__restrict__ row_len, i64 *__restrict__ partial) {
+    __shared__ i64 ws[8];
+    const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
+    i64 sum = 0;
+#pragma unroll 2
+    for (int j = 0; j < SCAN_CHUNK / 256; ++j) {
+        const i64 b = base + j * 256 + threadIdx.x;
+        if (b < B) {
+            u64 lo, hi;
+            u32 a;
+            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
+            int cell[N], act[N];
+            decode_state<N, WORDS>(sp, lo, hi, cell);
+            decode_action<N>(a, act);
+            i64 len = 1;
+            if (!is_terminal<N>(sp, cell, lo, hi)) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) len *= (i64)ENT_K(__ldg(sp.lut + cell[i] * 5 + act[i]));
+            }
+            row_len[b] = len;
+            sum += len;
+        }
+    }
+    i64 total;
+    block_scan_256(sum, ws, total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
 // =====================================================================================================
 // Expand: P[s][a] rows as CSR records (mapf_env.py:448-479)
 // =====================================================================================================

@@ -112,6 +112,13 @@ int64_t mapf_scan_scratch_bytes(int64_t B);
 int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64_t B, int64_t *row_ptr, void *scratch,
                    void *stream);
 
+/* mapf_count_rows + mapf_scan_rows in one call (one launch and one pass over row_len fewer): row_len[B] and
+ * row_ptr[B+1] are both written.  The _range form does the same for a table slab. */
+int mapf_count_scan_rows(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, int64_t *row_len,
+                         int64_t *row_ptr, void *scratch, void *stream);
+int mapf_count_scan_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_states, int64_t *row_len,
+                          int64_t *row_ptr, void *scratch, void *stream);
+
 /* P[s][a] for B pairs as CSR records in itertools.product order, agent 0 slowest (mapf_env.py:448-479):
  * record row_ptr[b] + j is the j-th element of P[states[b]][actions[b]].
  * next_state: state_words*8 bytes per record; prob, reward: f64; flags: MAPF_FLAG_DONE | MAPF_FLAG_COLLISION. */

@@ -84,8 +84,9 @@ def expand_case(tag, env, B_guess, rng, window=None):
     row_ptr = torch.empty(B + 1, dtype=torch.int64, device=DEV)
     scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device=DEV)
     s = eng._stream()
-    t_count = timed(lambda: check(lib().mapf_count_rows(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_len), s)))
-    t_scan = timed(lambda: check(lib().mapf_scan_rows(eng._h, _ptr(row_len), B, _ptr(row_ptr), _ptr(scratch), s)))
+    t_count = timed(lambda: check(lib().mapf_count_scan_rows(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_len), _ptr(row_ptr),
+                                                             _ptr(scratch), s)))
+    t_scan = 0.0  # fused into the count call
     total = int(row_ptr[-1].item())
     ns, prob, reward, flags = eng._alloc_records(total)
     t_exp = timed(lambda: check(lib().mapf_expand(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_ptr), _ptr(ns), _ptr(prob),
@@ -131,8 +132,9 @@ def c3_table():
     row_ptr = torch.empty(B + 1, dtype=torch.int64, device=DEV)
     scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device=DEV)
     s = eng._stream()
-    t_count = timed(lambda: check(lib().mapf_count_range(eng._h, C.byref(sb), n_states, _ptr(row_len), s)))
-    t_scan = timed(lambda: check(lib().mapf_scan_rows(eng._h, _ptr(row_len), B, _ptr(row_ptr), _ptr(scratch), s)))
+    t_count = timed(lambda: check(lib().mapf_count_scan_range(eng._h, C.byref(sb), n_states, _ptr(row_len), _ptr(row_ptr),
+                                                              _ptr(scratch), s)))
+    t_scan = 0.0  # fused into the count call
     total = int(row_ptr[-1].item())
     ns, prob, reward, flags = eng._alloc_records(total)
     t_exp = timed(lambda: check(lib().mapf_expand_range(eng._h, C.byref(sb), n_states, _ptr(row_ptr), _ptr(ns),
