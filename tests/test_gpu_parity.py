@@ -692,3 +692,32 @@ def test_batch_validation(torch):
         eng.step(st.to(torch.int32), good)
     with pytest.raises(ValueError):
         eng.step(st, good, uniforms=torch.zeros(8, 3, dtype=torch.float64, device=eng.torch_device))
+
+
+def test_next_row_error_paths(torch):
+    from gym_mapf_b200 import _native
+    spec, _ = G.load("rows_c2")
+    eng = make_engine(spec)
+    st = eng.states_from_ints([eng.s0] * 4)
+    ac = torch.zeros(4, dtype=torch.int32, device=eng.torch_device)
+    small_v = torch.zeros(10, dtype=torch.float64, device=eng.torch_device)
+    with pytest.raises(_native.NativeError):  # V does not cover the state space
+        eng.backup(st, ac, small_v, 0.9)
+    with pytest.raises(_native.NativeError):  # the slab leaves the state space
+        eng.backup_range(eng.nS - 1, 2, small_v, 0.9)
+    with pytest.raises(_native.NativeError):
+        eng.project(st, [0, 9])
+    with pytest.raises(_native.NativeError):
+        eng.greedy_bcast(torch.zeros((2, eng.nA), dtype=torch.float64, device=eng.torch_device), 0, [])
+    # two-word contexts have no value vector to back up against
+    spec4, _ = G.load("rows_c4")
+    eng4 = make_engine(spec4)
+    st4 = eng4.states_from_ints([eng4.s0] * 2)
+    with pytest.raises(_native.NativeError) as ei:
+        eng4.backup(st4, ac[:2], small_v, 0.9)
+    assert ei.value.code == _native.MAPF_ERR_UNSUPPORTED
+    # empty batches are fine everywhere
+    e_s, e_a = eng.new_states(0), ac[:0]
+    big_v = torch.zeros(8, dtype=torch.float64, device=eng.torch_device)
+    assert eng.predecessors(e_s)[0].tolist() == [0]
+    assert eng.project(e_s, [1, 0]).numel() == 0
