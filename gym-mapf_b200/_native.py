@@ -21,7 +21,9 @@ EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_mov
            "mapf_count_scan_range", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_rollout", "mapf_step_host",
            "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_greedy_bcast", "mapf_count_predecessors", "mapf_predecessors",
-           "mapf_projected_words", "mapf_project_states", "mapf_last_error", "mapf_version"]
+           "mapf_projected_words", "mapf_project_states", "mapf_parse_map_text", "mapf_ctx_create_from_text", "mapf_ctx_grid",
+           "mapf_group_create", "mapf_group_destroy", "mapf_group_size", "mapf_group_step", "mapf_last_error",
+           "mapf_version"]
 
 
 class MapfSpec(C.Structure):
@@ -98,6 +100,16 @@ def lib():
         L.mapf_predecessors.argtypes = [vp, vp, i64, vp, vp, vp]
         L.mapf_projected_words.argtypes = [vp, i32]
         L.mapf_project_states.argtypes = [vp, vp, i64, vp, i32, vp, vp]
+        L.mapf_parse_map_text.argtypes = [C.c_char_p, i64, i32, C.POINTER(i32), C.POINTER(i32), vp, i64]
+        L.mapf_ctx_create_from_text.argtypes = [C.c_char_p, i64, C.c_char_p, i64, i32, C.c_double, C.c_double, C.c_double,
+                                                C.c_double, i32, i32, C.POINTER(vp)]
+        L.mapf_ctx_grid.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
+        L.mapf_group_create.argtypes = [C.POINTER(vp), C.POINTER(i64), i32, C.POINTER(vp)]
+        L.mapf_group_destroy.argtypes = [vp]
+        L.mapf_group_destroy.restype = None
+        L.mapf_group_size.argtypes = [vp]
+        L.mapf_group_size.restype = i64
+        L.mapf_group_step.argtypes = [vp, vp, vp, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
         L.mapf_last_error.restype = C.c_char_p
         L.mapf_version.restype = C.c_char_p
         _lib = L
@@ -140,6 +152,41 @@ class Engine:
         self.torch_device = torch.device("cuda", self.device_index)
         h = C.c_void_p()
         check(lib().mapf_ctx_create(C.byref(spec), self.device_index, C.byref(h)))
+        self._adopt(h)
+
+    @classmethod
+    def from_text(cls, map_text, scen_text, n_agents, fail_prob, r_clash, r_goal, r_living, makespan, device=0):
+        """Context straight from the CONTENTS of a MovingAI .map and .scen file (bytes or str): the map is parsed on the
+        device (mapf_ctx_create_from_text)."""
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("gym_mapf_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback")
+        self = object.__new__(cls)
+        self.device_index = torch.device(device).index if not isinstance(device, int) else device
+        if self.device_index is None:
+            self.device_index = torch.cuda.current_device()
+        self.torch_device = torch.device("cuda", self.device_index)
+        map_b = map_text.encode("utf8") if isinstance(map_text, str) else bytes(map_text)
+        scen_b = scen_text.encode("utf8") if isinstance(scen_text, str) else bytes(scen_text)
+        h = C.c_void_p()
+        check(lib().mapf_ctx_create_from_text(map_b, len(map_b), scen_b, len(scen_b), int(n_agents), float(fail_prob),
+                                              float(r_clash), float(r_goal), float(r_living),
+                                              MAPF_MAKESPAN if makespan else MAPF_SOC, self.device_index, C.byref(h)))
+        self._adopt(h)
+        return self
+
+    def grid(self):
+        """(obstacles uint8[H, W], starts, goals) the context was built from (mapf_ctx_grid)."""
+        h, w = C.c_int32(), C.c_int32()
+        check(lib().mapf_ctx_grid(self._h, C.byref(h), C.byref(w), None, None, None))
+        obstacles = np.zeros((h.value, w.value), np.uint8)
+        start_rc = np.zeros(2 * self.n, np.int32)
+        goal_rc = np.zeros(2 * self.n, np.int32)
+        check(lib().mapf_ctx_grid(self._h, None, None, _ptr(obstacles), _ptr(start_rc), _ptr(goal_rc)))
+        pairs = lambda a: tuple((int(a[2 * i]), int(a[2 * i + 1])) for i in range(self.n))  # noqa: E731
+        return obstacles, pairs(start_rc), pairs(goal_rc)
+
+    def _adopt(self, h):
         self._h = h
         info = MapfInfo()
         check(lib().mapf_ctx_info(self._h, C.byref(info)))
@@ -401,4 +448,65 @@ class Engine:
             check(words)
         out = torch.empty((B,) if words == 1 else (B, 2), dtype=torch.int64, device=self.torch_device)
         check(lib().mapf_project_states(self._h, _ptr(states), B, _ptr(agents), len(agents), _ptr(out), self._stream()))
+        return out
+
+
+def parse_map_text(map_text, device=0):
+    """uint8[H, W] obstacle mask (1 = '@') of a MovingAI .map file's CONTENTS, parsed on the device
+    (mapf_parse_map_text; reference utils.py:33-37 + grid.py:17-25).  KeyError for an unknown cell character."""
+    data = map_text.encode("utf8") if isinstance(map_text, str) else bytes(map_text)
+    h, w = C.c_int32(), C.c_int32()
+    out = np.zeros(max(1, len(data)), np.uint8)
+    check(lib().mapf_parse_map_text(data, len(data), int(device), C.byref(h), C.byref(w), _ptr(out), out.size))
+    return out[:h.value * w.value].reshape(h.value, w.value).copy()
+
+
+class Group:
+    """A heterogeneous env batch (mapf_group): counts[i] envs of engines[i], concatenated; one launch steps them all."""
+
+    def __init__(self, engines, counts):
+        if len(engines) != len(counts) or not engines:
+            raise ValueError("one env count per engine")
+        self.engines = list(engines)
+        self.counts = [int(c) for c in counts]
+        self.n, self.words = engines[0].n, engines[0].words
+        self.torch_device = engines[0].torch_device
+        self.device_index = engines[0].device_index
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        cnt = (C.c_int64 * len(counts))(*self.counts)
+        h = C.c_void_p()
+        check(lib().mapf_group_create(arr, cnt, len(engines), C.byref(h)))
+        self._h = h
+        self.size = int(lib().mapf_group_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mapf_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None):
+        import torch
+        B, dev = self.size, self.torch_device
+        shape = (B,) if self.words == 1 else (B, 2)
+        if states.dtype is not torch.int64 or tuple(states.shape) != shape or not states.is_contiguous() or states.device != dev:
+            raise ValueError("states must be a contiguous int64 tensor of shape %s on %s" % (shape, dev))
+        if actions.dtype is not torch.int32 or tuple(actions.shape) != (B,) or not actions.is_contiguous() or actions.device != dev:
+            raise ValueError("actions must be a contiguous int32 tensor of shape (%d,) on %s" % (B, dev))
+        if uniforms is not None and (uniforms.dtype is not torch.float64 or tuple(uniforms.shape) != (B, self.n)
+                                     or not uniforms.is_contiguous() or uniforms.device != dev):
+            raise ValueError("uniforms must be a contiguous float64 tensor of shape (%d, %d) on %s" % (B, self.n, dev))
+        if out is None:
+            out = (torch.empty(shape, dtype=torch.int64, device=dev), torch.empty(B, dtype=torch.float64, device=dev),
+                   torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.bool, device=dev),
+                   torch.empty(B, dtype=torch.bool, device=dev))
+        ns, reward, prob, done, coll = out
+        check(lib().mapf_group_step(self._h, _ptr(states), _ptr(actions), _ptr(uniforms), seed, step_index, env_offset,
+                                    OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
+                                    _ptr(coll), torch.cuda.current_stream(self.device_index).cuda_stream))
         return out

@@ -1082,3 +1082,291 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
     for (int h = 0; h < parts; ++h) CUDA_TRY(cudaStreamSynchronize(ctx->hs[h]));
     return MAPF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// on-disk formats: MovingAI .map text parsed on the device, .scen text on the host
+// ---------------------------------------------------------------------------------------------------------------
+#include "mapf_parse.cuh"
+
+// int() of one tab-separated scenario field: optional surrounding whitespace, optional sign, decimal digits
+static bool parse_int_field(const char *b, const char *e, long long *out) {
+    while (b < e && ((unsigned char)*b <= 32)) ++b;
+    while (e > b && ((unsigned char)e[-1] <= 32)) --e;
+    if (b >= e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; ++b; }
+    if (b >= e) return false;
+    long long v = 0;
+    for (; b < e; ++b) {
+        if (*b == '_' && b + 1 < e) continue;  // Python accepts 1_000
+        if (*b < '0' || *b > '9') return false;
+        v = v * 10 + (*b - '0');
+        if (v > (1ll << 40)) return false;
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+// parse_scen_file (utils.py:8-30): skip the "version" line; every further line must have exactly nine tab-separated
+// fields (the reference's tuple unpacking raises ValueError otherwise); fields 4..7 are used AS (row, col) pairs in
+// file order; stops after n_agents lines or at the end of the file (`n_agents` is truncated, utils.py:123).
+static int parse_scen_text(const char *text, int64_t len, int n_agents, int32_t *start_rc, int32_t *goal_rc, int *n_found) {
+    int64_t p = 0;
+    auto next_line = [&](int64_t &b, int64_t &e) -> bool {  // [b, e) without the terminator; universal newlines
+        if (p >= len) return false;
+        b = p;
+        while (p < len && text[p] != '\n' && text[p] != '\r') ++p;
+        e = p;
+        if (p < len) { if (text[p] == '\r' && p + 1 < len && text[p + 1] == '\n') p += 2; else p += 1; }
+        return true;
+    };
+    int64_t b, e;
+    if (!next_line(b, e)) return fail(MAPF_ERR_INVALID, "scenario text is empty (StopIteration in the reference)");
+    int got = 0;
+    while (got < n_agents && next_line(b, e)) {
+        int64_t fb[10];
+        int nf = 0;
+        fb[0] = b;
+        for (int64_t q = b; q < e; ++q)
+            if (text[q] == '\t') { if (nf < 9) fb[++nf] = q + 1; else ++nf; }
+        const int fields = nf + 1;
+        if (fields != 9)
+            return fail(MAPF_ERR_INVALID, "scenario line %d has %d tab-separated fields, expected 9", got + 2, fields);
+        fb[9] = e + 1;
+        long long v[4];
+        for (int k = 0; k < 4; ++k)
+            if (!parse_int_field(text + fb[4 + k], text + fb[5 + k] - 1, &v[k]))
+                return fail(MAPF_ERR_INVALID, "scenario line %d: field %d is not an integer", got + 2, 4 + k);
+        start_rc[2 * got] = (int32_t)v[0]; start_rc[2 * got + 1] = (int32_t)v[1];
+        goal_rc[2 * got] = (int32_t)v[2]; goal_rc[2 * got + 1] = (int32_t)v[3];
+        ++got;
+    }
+    *n_found = got;
+    return MAPF_OK;
+}
+
+extern "C" int mapf_parse_map_text(const char *map_text, int64_t map_len, int device, int32_t *height, int32_t *width,
+                                   uint8_t *obstacles, int64_t obstacles_cap) {
+    if (!map_text || map_len < 0 || !height || !width) return fail(MAPF_ERR_INVALID, "mapf_parse_map_text: bad argument");
+    if (map_len > (64ll << 20)) return fail(MAPF_ERR_UNSUPPORTED, "map text of %lld bytes: at most 64 MiB", (long long)map_len);
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1 || device < 0 || device >= n_dev)
+        return fail(MAPF_ERR_NO_DEVICE, "CUDA device %d is not available (%d devices): there is no CPU fallback", device, n_dev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MAPF_ERR_CUDA, "cannot select device %d", device);
+    const u32 len = (u32)map_len;
+    // one allocation: text | line_start[len + 2] | row_begin[len + 1] | row_len[len + 1] | obstacles[len] | header
+    const size_t o_text = 0, o_ls = (o_text + len + 15) & ~(size_t)15, o_rb = o_ls + 4 * ((size_t)len + 2),
+                 o_rl = o_rb + 4 * ((size_t)len + 1), o_ob = o_rl + 4 * ((size_t)len + 1),
+                 o_hdr = (o_ob + len + 15) & ~(size_t)15, total = o_hdr + sizeof(ParsedMapHeader);
+    unsigned char *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, total));
+    struct Free { unsigned char *p; ~Free() { cudaFree(p); } } guard_free{d};
+    if (len) CUDA_TRY(cudaMemcpy(d + o_text, map_text, len, cudaMemcpyHostToDevice));
+    k_parse_map<<<1, PARSE_THREADS>>>(d + o_text, len, (u32 *)(d + o_ls), (u32 *)(d + o_rb), (u32 *)(d + o_rl), d + o_ob,
+                                      (ParsedMapHeader *)(d + o_hdr));
+    CUDA_TRY(cudaGetLastError());
+    ParsedMapHeader hdr;
+    CUDA_TRY(cudaMemcpy(&hdr, d + o_hdr, sizeof(hdr), cudaMemcpyDeviceToHost));
+    if (hdr.H < 1 || hdr.W < 1)
+        return fail(MAPF_ERR_INVALID, "map text has %d lines: no grid rows behind the 4 header lines", hdr.n_lines);
+    if (hdr.bad_pos != 0xffffffffu) {  // CHAR_TO_CELL[char] raises KeyError (grid.py:21)
+        if (hdr.bad_char >= 32 && hdr.bad_char < 127) return fail(MAPF_ERR_KEY, "'%c'", (int)hdr.bad_char);
+        return fail(MAPF_ERR_KEY, "'\\x%02x'", hdr.bad_char);
+    }
+    if (hdr.ragged)
+        return fail(MAPF_ERR_INVALID, "grid row %d is not %d cells wide like row 0", hdr.ragged - 1, hdr.W);
+    *height = hdr.H;
+    *width = hdr.W;
+    if (obstacles) {
+        if (obstacles_cap < (int64_t)hdr.H * hdr.W)
+            return fail(MAPF_ERR_INVALID, "obstacle buffer of %lld bytes for a %dx%d grid", (long long)obstacles_cap, hdr.H, hdr.W);
+        CUDA_TRY(cudaMemcpy(obstacles, d + o_ob, (size_t)hdr.H * hdr.W, cudaMemcpyDeviceToHost));
+    }
+    return MAPF_OK;
+}
+
+extern "C" int mapf_ctx_create_from_text(const char *map_text, int64_t map_len, const char *scen_text, int64_t scen_len,
+                                         int32_t n_agents, double fail_prob, double reward_of_clash, double reward_of_goal,
+                                         double reward_of_living, int32_t criterion, int device, mapf_ctx **out) {
+    if (!map_text || !scen_text || map_len < 0 || scen_len < 0 || !out)
+        return fail(MAPF_ERR_INVALID, "mapf_ctx_create_from_text: bad argument");
+    *out = nullptr;
+    if (n_agents < 1) return fail(MAPF_ERR_INVALID, "n_agents = %d", n_agents);
+    int32_t H = 0, W = 0;
+    std::vector<uint8_t> obstacles((size_t)map_len + 1);
+    int rc = mapf_parse_map_text(map_text, map_len, device, &H, &W, obstacles.data(), (int64_t)obstacles.size());
+    if (rc) return rc;
+    const int want = n_agents < 4096 ? n_agents : 4096;
+    std::vector<int32_t> start_rc(2 * (size_t)want), goal_rc(2 * (size_t)want);
+    int found = 0;
+    rc = parse_scen_text(scen_text, scen_len, want, start_rc.data(), goal_rc.data(), &found);
+    if (rc) return rc;
+    if (found < 1) return fail(MAPF_ERR_INVALID, "the scenario holds no agent");
+    mapf_spec spec;
+    memset(&spec, 0, sizeof(spec));
+    spec.height = H; spec.width = W;
+    spec.obstacles = obstacles.data();
+    spec.n_agents = found;  // n_agents = len(agents_goals) (utils.py:123)
+    spec.start_rc = start_rc.data();
+    spec.goal_rc = goal_rc.data();
+    spec.fail_prob = fail_prob;
+    spec.reward_of_clash = reward_of_clash; spec.reward_of_goal = reward_of_goal; spec.reward_of_living = reward_of_living;
+    spec.criterion = criterion;
+    return mapf_ctx_create(&spec, device, out);
+}
+
+extern "C" int mapf_ctx_grid(const mapf_ctx *ctx, int32_t *height, int32_t *width, uint8_t *obstacles, int32_t *start_rc,
+                             int32_t *goal_rc) {
+    if (!ctx) return fail(MAPF_ERR_INVALID, "mapf_ctx_grid: NULL context");
+    const int H = ctx->sp.H, W = ctx->sp.Wd;
+    if (height) *height = H;
+    if (width) *width = W;
+    if (obstacles) {
+        memset(obstacles, 1, (size_t)H * W);
+        for (int i = 0; i < ctx->sp.L; ++i)
+            obstacles[(size_t)(ctx->h_cell_rc[i] >> 16) * W + (ctx->h_cell_rc[i] & 0xffffu)] = 0;
+    }
+    for (int i = 0; i < ctx->sp.n; ++i) {
+        const u32 s = ctx->h_cell_rc[ctx->sp.start[i]], g = ctx->h_cell_rc[ctx->sp.goal[i]];
+        if (start_rc) { start_rc[2 * i] = (int32_t)(s >> 16); start_rc[2 * i + 1] = (int32_t)(s & 0xffffu); }
+        if (goal_rc) { goal_rc[2 * i] = (int32_t)(g >> 16); goal_rc[2 * i + 1] = (int32_t)(g & 0xffffu); }
+    }
+    return MAPF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// heterogeneous batches: one launch steps envs of several specs
+// ---------------------------------------------------------------------------------------------------------------
+struct mapf_group {
+    int device = 0;
+    int n = 0, words = 0, n_specs = 0;
+    int threads = 512, grid = 0;
+    int64_t B = 0;
+    u32 n_tiles = 0, spec_off = 0;
+    size_t smem = 0;
+    bool philox_ok = true;
+    const void *fn_philox = nullptr, *fn_tape = nullptr;
+    DevSpec *d_specs = nullptr;
+    GroupTile *d_tiles = nullptr;
+    std::vector<int64_t> seg_begin;
+};
+
+extern "C" void mapf_group_destroy(mapf_group *g) {
+    if (!g) return;
+    {
+        DeviceGuard guard(g->device);
+        cudaFree(g->d_specs);
+        cudaFree(g->d_tiles);
+    }
+    delete g;
+}
+
+extern "C" int mapf_group_create(mapf_ctx *const *ctxs, const int64_t *env_counts, int32_t n_specs, mapf_group **out) {
+    if (!ctxs || !env_counts || n_specs < 1 || !out) return fail(MAPF_ERR_INVALID, "mapf_group_create: bad argument");
+    *out = nullptr;
+    for (int i = 0; i < n_specs; ++i)
+        if (!ctxs[i] || env_counts[i] < 0) return fail(MAPF_ERR_INVALID, "mapf_group_create: bad spec %d", i);
+    const mapf_ctx *c0 = ctxs[0];
+    size_t smem_max = 0;
+    int64_t B = 0;
+    bool philox_ok = true;
+    for (int i = 0; i < n_specs; ++i) {
+        const mapf_ctx *c = ctxs[i];
+        if (c->device != c0->device) return fail(MAPF_ERR_INVALID, "spec %d lives on device %d, spec 0 on %d", i, c->device, c0->device);
+        if (c->sp.n != c0->sp.n || c->sp.words != c0->sp.words)
+            return fail(MAPF_ERR_UNSUPPORTED,
+                        "spec %d has %d agents and %d-word states, spec 0 has %d and %d: one group = one agent count and "
+                        "state width (step other specs with their own mapf_step)",
+                        i, c->sp.n, c->sp.words, c0->sp.n, c0->sp.words);
+        if (!c->sp.lut_smem)
+            return fail(MAPF_ERR_UNSUPPORTED, "spec %d: its move table is not staged in shared memory (too many cells); step it "
+                                              "with its own mapf_step", i);
+        if (c->sp.smem_window != c0->sp.smem_window) return fail(MAPF_ERR_INVALID, "specs were built for different shared-memory windows");
+        if (c->smem_base > smem_max) smem_max = c->smem_base;
+        philox_ok = philox_ok && c->philox_ok;
+        B += env_counts[i];
+    }
+    if (B >= (1ll << 31)) return fail(MAPF_ERR_UNSUPPORTED, "%lld envs: a group holds fewer than 2**31", (long long)B);
+    mapf_group *g = new (std::nothrow) mapf_group();
+    if (!g) return fail(MAPF_ERR_INVALID, "out of host memory");
+    g->device = c0->device; g->n = c0->sp.n; g->words = c0->sp.words; g->n_specs = n_specs; g->B = B;
+    g->philox_ok = philox_ok;
+    g->fn_philox = c0->ks.step_group_philox;
+    g->fn_tape = c0->ks.step_group_tape;
+    g->spec_off = (u32)((smem_max + 15) & ~(size_t)15);
+    g->smem = g->spec_off + ((sizeof(DevSpec) + 15) & ~(size_t)15);
+    std::vector<DevSpec> specs(n_specs);
+    std::vector<GroupTile> tiles;
+    g->seg_begin.resize((size_t)n_specs + 1);
+    int64_t at = 0;
+    for (int i = 0; i < n_specs; ++i) {
+        specs[i] = ctxs[i]->sp;
+        g->seg_begin[i] = at;
+        for (int64_t o = 0; o < env_counts[i]; o += GROUP_TILE) {
+            GroupTile t;
+            t.spec = (u32)i; t.begin = (u32)(at + o);
+            t.count = (u32)(env_counts[i] - o < GROUP_TILE ? env_counts[i] - o : GROUP_TILE);
+            t.pad = 0;
+            tiles.push_back(t);
+        }
+        at += env_counts[i];
+    }
+    g->seg_begin[n_specs] = at;
+    g->n_tiles = (u32)tiles.size();
+    DeviceGuard guard(g->device);
+#define GRP_TRY(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            int _rc = fail(MAPF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            mapf_group_destroy(g);                                                                     \
+            return _rc;                                                                                \
+        }                                                                                              \
+    } while (0)
+    if (!g->fn_philox || !g->fn_tape) { mapf_group_destroy(g); return fail(MAPF_ERR_UNSUPPORTED, "no grouped step kernel for this spec"); }
+    GRP_TRY(cudaMalloc(&g->d_specs, sizeof(DevSpec) * (size_t)n_specs));
+    GRP_TRY(cudaMemcpy(g->d_specs, specs.data(), sizeof(DevSpec) * (size_t)n_specs, cudaMemcpyHostToDevice));
+    GRP_TRY(cudaMalloc(&g->d_tiles, sizeof(GroupTile) * (tiles.size() + 1)));
+    if (!tiles.empty())
+        GRP_TRY(cudaMemcpy(g->d_tiles, tiles.data(), sizeof(GroupTile) * tiles.size(), cudaMemcpyHostToDevice));
+    int grid_p = 0, grid_t = 0;
+    for (const void *fn : {g->fn_philox, g->fn_tape})
+        if (g->smem > 48 * 1024) GRP_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
+    cudaDeviceProp prop;
+    GRP_TRY(cudaGetDeviceProperties(&prop, g->device));
+    if (g->smem > (size_t)prop.sharedMemPerBlockOptin) {
+        mapf_group_destroy(g);
+        return fail(MAPF_ERR_UNSUPPORTED, "the group's largest image needs %zu B of shared memory", g->smem);
+    }
+    int rc = occupancy_grid(g->fn_philox, g->threads, g->smem, c0->info.sm_count, &grid_p);
+    if (!rc) rc = occupancy_grid(g->fn_tape, g->threads, g->smem, c0->info.sm_count, &grid_t);
+    if (rc) { mapf_group_destroy(g); return rc; }
+    g->grid = grid_p < grid_t ? grid_p : grid_t;
+    *out = g;
+    return MAPF_OK;
+}
+
+extern "C" int mapf_group_step(const mapf_group *g, const void *states, const int32_t *actions, const double *uniforms,
+                               uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
+                               double *reward, double *prob, uint8_t *done, uint8_t *collision, void *stream) {
+    if (!g) return fail(MAPF_ERR_INVALID, "mapf_group_step: NULL group");
+    if (g->B == 0) return MAPF_OK;
+    if (!states || !actions || !next_states || !reward || !prob || !done || !collision)
+        return fail(MAPF_ERR_INVALID, "mapf_group_step: NULL buffer");
+    if (!uniforms && !g->philox_ok)
+        return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
+    DeviceGuard guard(g->device);
+    PhiloxKeys keys = make_keys(seed);
+    const DevSpec *specs = g->d_specs;
+    const GroupTile *tiles = g->d_tiles;
+    u32 n_tiles = g->n_tiles, spec_off = g->spec_off, op = options;
+    u64 st = step_index, e0 = (u64)env_offset;
+    void *args[] = {&specs, &tiles, &n_tiles, &spec_off, &keys, &states, &actions, &uniforms, &st, &e0, &op, &next_states,
+                    &reward, &prob, &done, &collision};
+    const int grid = (int)(n_tiles < (u32)g->grid ? n_tiles : (u32)g->grid);
+    LAUNCH(uniforms ? g->fn_tape : g->fn_philox, grid, g->threads, g->smem, stream, args);
+    return MAPF_OK;
+}
+
+extern "C" int64_t mapf_group_size(const mapf_group *g) { return g ? g->B : -1; }

@@ -14,6 +14,10 @@ static void fill(KernelSet *k) {
     k->step_tape = (const void *)k_step<N, W, LUTS, true, 1>;
     k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false>;
     k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true>;
+    if (LUTS) {
+        k->step_group_philox = (const void *)k_step_group<N, W, false>;
+        k->step_group_tape = (const void *)k_step_group<N, W, true>;
+    }
     k->expand = (const void *)k_expand<N, W, LUTS, false>;
     k->expand_range = (const void *)k_expand<N, W, LUTS, true>;
     k->count = (const void *)k_count<N, W, false>;

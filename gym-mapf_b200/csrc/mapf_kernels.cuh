@@ -1227,3 +1227,90 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
     }
     if (!ready) tables_wait<LUTS>(smem);
 }
+
+// =====================================================================================================
+// Heterogeneous batches: envs of DIFFERENT specs (grid, starts/goals, rewards) in one launch
+// =====================================================================================================
+// The batch is a concatenation of per-spec segments, cut into tiles of at most GROUP_TILE envs.  The tiles are dealt
+// out in contiguous runs, one run per CTA, so a CTA changes spec at most (specs inside its run) times; on a change it
+// re-stages the spec's shared-memory image with one bulk copy (the images of all specs of a group were built for the
+// same shared-memory window) and copies the spec's DevSpec behind the largest image, from where the device functions
+// read it instead of the constant bank.  Same agent count, state width and per-env semantics as k_step; the Philox
+// counter is the env's index in the whole batch.
+struct GroupTile {
+    u32 spec, begin, count, pad;
+};
+#define GROUP_TILE 1024
+
+template <int N, int WORDS, bool TAPE>
+__global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
+k_step_group(const DevSpec *__restrict__ specs, const GroupTile *__restrict__ tiles, u32 n_tiles, u32 spec_off,
+             PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, const double *__restrict__ uniforms,
+             u64 step, u64 env0, u32 opts, u64 *next_states, double *__restrict__ reward, double *__restrict__ prob,
+             u8 *__restrict__ done, u8 *__restrict__ coll) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    DevSpec *ssp = reinterpret_cast<DevSpec *>(smem + spec_off);
+    const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    SmemTables tb;
+    tb.base = smem_u32(smem);
+    tb.lut = smem_u32(smem + MAPF_SMEM_LUT);
+    tb.act0 = tb.lut;
+    tb.lut_g = nullptr;
+    const u32 t0 = (u32)((u64)n_tiles * blockIdx.x / gridDim.x), t1 = (u32)((u64)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    u32 cur = 0xffffffffu, phase = 0;
+    for (u32 t = t0; t < t1; ++t) {
+        const GroupTile tl = tiles[t];
+        if (tl.spec != cur) {
+            __syncthreads();  // every thread is done with the previous spec's tables (and sees the barrier's init)
+            const u32 *src = reinterpret_cast<const u32 *>(specs + tl.spec);
+            u32 *dst = reinterpret_cast<u32 *>(ssp);
+            for (u32 i = threadIdx.x; i < sizeof(DevSpec) / 4; i += blockDim.x) dst[i] = src[i];
+            if (threadIdx.x == 0) {
+                const DevSpec &g = specs[tl.spec];
+                if (tb.base != g.smem_window) __trap();  // the action table was built for another window address
+                const u32 bytes = g.image_bytes;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                for (u32 off = 0; off < bytes;) {
+                    const u32 piece = bytes - off < 32768u ? bytes - off : 32768u;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(smem + MAPF_SMEM_IMG + off)),
+                                 "l"(g.image + off), "r"(piece), "r"(bar)
+                                 : "memory");
+                    off += piece;
+                }
+            }
+            __syncthreads();  // the DevSpec copy is complete
+            u32 ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok)
+                             : "r"(bar), "r"(phase)
+                             : "memory");
+            } while (!ok);
+            phase ^= 1u;
+            cur = tl.spec;
+        }
+        const DevSpec &sp = *ssp;
+        for (u32 i = threadIdx.x; i < tl.count; i += blockDim.x) {
+            const u32 b = tl.begin + i;
+            EnvIn<N> in;
+            load_state<WORDS>(states, b, in.lo, in.hi);
+            const u32 a = (u32)actions[b];
+            decode_state<N, WORDS, true>(sp, in.lo, in.hi, in.cell);
+            if (!TAPE) env_draws<N>(keys, env0 + (u64)b, step, in);
+            load_actions<N>(sp, tb, a, in.actv);
+            int nxt[N];
+            const EnvOut o = env_step<N, WORDS, true, TAPE>(sp, tb, in, TAPE ? uniforms + (size_t)b * N : nullptr, opts, nxt);
+            store_state<WORDS>(next_states, b, o.lo, o.hi);
+            reward[b] = o.reward;
+            prob[b] = o.prob;
+            done[b] = (u8)o.done;
+            coll[b] = (u8)o.coll;
+        }
+    }
+}

@@ -67,6 +67,25 @@ def create_mapf_env(map_name, scen_id, n_agents, fail_prob, reward_of_clash, rew
                    optimization_criteria, **kwargs)
 
 
+def create_mapf_env_from_text(map_text, scen_text, n_agents, fail_prob, reward_of_clash, reward_of_goal, reward_of_living,
+                              optimization_criteria, device=None):
+    """`create_mapf_env` for file CONTENTS (bytes or str) instead of a shipped map name: the .map text is parsed on the
+    GPU straight into the obstacle bitmap and move table (C ABI `mapf_ctx_create_from_text`; same rules as
+    utils.py:8-37 and grid.py:17-25, same KeyError for an unknown cell character or a start/goal on an obstacle).
+    The returned MapfEnv's grid / starts / goals are read back from the device context."""
+    from .. import _native
+    from .mapf_env import OptimizationCriteria
+    eng = _native.Engine.from_text(map_text, scen_text, n_agents, fail_prob, reward_of_clash, reward_of_goal,
+                                   reward_of_living, optimization_criteria == OptimizationCriteria.Makespan,
+                                   device=0 if device is None else device)
+    obstacles, starts, goals = eng.grid()
+    grid = MapfGrid(["".join("@" if v else "." for v in row) for row in obstacles])
+    env = MapfEnv(grid, eng.n, starts, goals, fail_prob, reward_of_clash, reward_of_goal, reward_of_living,
+                  optimization_criteria, device=device)
+    env._engine_obj = eng
+    return env
+
+
 def get_local_view(env: MapfEnv, agent_indexes: list, **kwargs):
     """The env restricted to a subset of its agents (utils.py:138-157)."""
     keep = [i for i in range(env.n_agents) if i in agent_indexes]

@@ -171,3 +171,88 @@ class VecMapfEnv:
     def project(self, states, agent_indexes):
         """The joint states as `get_local_view(env, agent_indexes)` numbers them (reference utils.py:138-157)."""
         return self.engine.project(states, agent_indexes)
+
+
+class MultiMapVecEnv:
+    """A heterogeneous batch: counts[i] copies of envs[i] -- different grids, scenarios, rewards or criteria per
+    segment -- stepped together.  Env b of the concatenated batch belongs to the spec whose
+    segment [offsets[i], offsets[i + 1]) holds b.
+
+    Specs that agree in agent count and state width (and whose move tables fit shared memory) are stepped by ONE
+    launch of the grouped kernel (`mapf_group_step`); a batch that mixes agent counts or state widths is split into
+    one group per (agent count, width) class, each over its own contiguous slice, so every class must be contiguous
+    in `envs`.  Per-env semantics are those of `VecMapfEnv.step` / `MapfEnv.step` (reference mapf_env.py:237-266).
+    State tensors are int64[B] (or int64[B, 2] when every spec needs two words)."""
+
+    def __init__(self, envs, counts, seed=0, auto_reset=True):
+        import torch
+        from .. import _native
+        if len(envs) != len(counts) or not envs:
+            raise ValueError("one env count per env")
+        self._torch = torch
+        self.envs = list(envs)
+        self.counts = [int(c) for c in counts]
+        self.offsets = [0]
+        for c in self.counts:
+            self.offsets.append(self.offsets[-1] + c)
+        self.num_envs = self.offsets[-1]
+        self.seed, self.auto_reset, self.step_count = int(seed), bool(auto_reset), 0
+        engines = [e.engine for e in self.envs]
+        self.device = engines[0].torch_device
+        words = {e.words for e in engines}
+        if len(words) != 1:
+            raise ValueError("all specs of a MultiMapVecEnv must have the same state width (1 or 2 words)")
+        self.words = words.pop()
+        # contiguous runs of compatible specs -> one mapf_group each; a spec whose table is not staged steps alone
+        self._parts = []  # (first env, last env, Group or Engine)
+        i = 0
+        while i < len(engines):
+            if not engines[i].moves_in_smem:
+                self._parts.append((self.offsets[i], self.offsets[i + 1], engines[i]))
+                i += 1
+                continue
+            j = i
+            while j < len(engines) and engines[j].moves_in_smem and engines[j].n == engines[i].n:
+                j += 1
+            self._parts.append((self.offsets[i], self.offsets[j], _native.Group(engines[i:j], self.counts[i:j])))
+            i = j
+        shape = (self.num_envs,) if self.words == 1 else (self.num_envs, 2)
+        self.states = torch.empty(shape, dtype=torch.int64, device=self.device)
+        self.reset()
+
+    def spec_of(self, b):
+        """Index into `envs` of the spec env b belongs to."""
+        import bisect
+        return bisect.bisect_right(self.offsets, int(b)) - 1
+
+    def reset(self):
+        for i, env in enumerate(self.envs):
+            lo, hi = self.offsets[i], self.offsets[i + 1]
+            if hi > lo:
+                self.states[lo:hi] = env.engine.states_from_ints([env.engine.s0])
+        return self.states
+
+    def set_states(self, states):
+        self.states.copy_(states)
+
+    def step(self, actions, uniforms=None):
+        """One joint step of every env: (next_states, rewards, dones, {"prob", "collision"}).  `actions` is int32[B];
+        `uniforms` (float64[B, n], groups of one agent count only) replays given draws bit-exactly."""
+        torch = self._torch
+        B, dev = self.num_envs, self.device
+        ns = torch.empty_like(self.states)
+        reward = torch.empty(B, dtype=torch.float64, device=dev)
+        prob = torch.empty(B, dtype=torch.float64, device=dev)
+        done = torch.empty(B, dtype=torch.bool, device=dev)
+        coll = torch.empty(B, dtype=torch.bool, device=dev)
+        if uniforms is not None and len(self._parts) != 1:
+            raise ValueError("uniforms can only be replayed when every spec has the same agent count")
+        for lo, hi, part in self._parts:
+            if hi == lo:
+                continue
+            out = (ns[lo:hi], reward[lo:hi], prob[lo:hi], done[lo:hi], coll[lo:hi])
+            part.step(self.states[lo:hi], actions[lo:hi], uniforms=uniforms, seed=self.seed, step_index=self.step_count,
+                      env_offset=lo, auto_reset=self.auto_reset, out=out)
+        self.states = ns
+        self.step_count += 1
+        return ns, reward, done, {"prob": prob, "collision": coll}

@@ -199,6 +199,43 @@ int mapf_projected_words(const mapf_ctx *ctx, int32_t n_sub);
 int mapf_project_states(const mapf_ctx *ctx, const void *states, int64_t B, const int32_t *agents, int32_t n_sub,
                         void *out_states, void *stream);
 
+/* ---- on-disk formats and heterogeneous batches ------------------------------------------- */
+
+/* parse_map_file + MapfGrid.__init__ (utils.py:33-37, grid.py:9-25) on the DEVICE: `map_text` (HOST memory, the raw
+ * bytes of a MovingAI .map file) is copied to the device, where one kernel finds the lines, drops the 4 header lines,
+ * strip()s each grid row and classifies its characters.  *height / *width receive the grid size; `obstacles` (HOST,
+ * may be NULL, capacity obstacles_cap bytes) the row-major cells, 1 = '@'.  A character other than '.' / '@' returns
+ * MAPF_ERR_KEY with the character as the message (the reference's KeyError, grid.py:21).  Synchronous. */
+int mapf_parse_map_text(const char *map_text, int64_t map_len, int device, int32_t *height, int32_t *width,
+                        uint8_t *obstacles, int64_t obstacles_cap);
+
+/* create_mapf_env for file CONTENTS (utils.py:119-135): the map text goes through mapf_parse_map_text, the scenario
+ * text through parse_scen_file's rules (utils.py:8-30: first line skipped, nine tab-separated fields per line, fields
+ * 4..7 used as (row, col) of start and goal, the first n_agents lines, n_agents truncated to what the file holds),
+ * then mapf_ctx_create.  Both texts are HOST memory. */
+int mapf_ctx_create_from_text(const char *map_text, int64_t map_len, const char *scen_text, int64_t scen_len,
+                              int32_t n_agents, double fail_prob, double reward_of_clash, double reward_of_goal,
+                              double reward_of_living, int32_t criterion, int device, mapf_ctx **out);
+
+/* What a context was built from: grid size, row-major obstacle bytes (HOST, height*width), and the (row, col) of every
+ * agent's start and goal (HOST, 2*n_agents ints each).  Any output may be NULL. */
+int mapf_ctx_grid(const mapf_ctx *ctx, int32_t *height, int32_t *width, uint8_t *obstacles, int32_t *start_rc,
+                  int32_t *goal_rc);
+
+/* A heterogeneous env batch: env_counts[i] envs of spec ctxs[i], concatenated in this order (spec i owns the envs
+ * [sum(env_counts[:i]), sum(env_counts[:i+1]))).  All specs must live on one device and agree in agent count and
+ * state width, and their move tables must be staged in shared memory (mapf_info.moves_in_smem); anything else is
+ * MAPF_ERR_UNSUPPORTED -- step such specs with their own mapf_step.  The contexts must outlive the group. */
+typedef struct mapf_group mapf_group;
+int mapf_group_create(mapf_ctx *const *ctxs, const int64_t *env_counts, int32_t n_specs, mapf_group **out);
+void mapf_group_destroy(mapf_group *group);
+int64_t mapf_group_size(const mapf_group *group);
+/* MapfEnv.step (mapf_env.py:237-266) for every env of the group in ONE launch; buffers and semantics as mapf_step,
+ * indexed by the env's position in the concatenated batch (which also keys its Philox stream). */
+int mapf_group_step(const mapf_group *group, const void *states, const int32_t *actions, const double *uniforms,
+                    uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
+                    double *reward, double *prob, uint8_t *done, uint8_t *collision, void *stream);
+
 const char *mapf_last_error(void);
 const char *mapf_version(void);
 

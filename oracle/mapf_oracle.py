@@ -213,3 +213,44 @@ def spec_from_reference_env(env, soc):
     rows = ["".join("." if (r, c) in free else "@" for c in range(w)) for r in range(h)]
     return OracleSpec(rows, env.n_agents, env.agents_starts, env.agents_goals, env.fail_prob,
                       env.reward_of_clash, env.reward_of_goal, env.reward_of_living, soc)
+
+
+# ---- on-disk formats; pinned by tests/golden/formats.json (oracle/make_golden_formats.py) -------
+def parse_map_text(data: bytes):
+    """Rows ('.'/'@' strings) of a MovingAI .map file's contents: text-mode `readlines()[4:]` (`utils.py:33-37`, universal
+    newlines), every line `strip()`ped and every character looked up in CHAR_TO_CELL (`grid.py:9-13,19-22`: KeyError for
+    anything but '.' and '@')."""
+    text = data.decode("latin-1").replace("\r\n", "\n").replace("\r", "\n")
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()  # readlines() has no empty line behind a final terminator
+    rows = []
+    for line in lines[4:]:
+        line = line.strip()
+        for ch in line:
+            if ch not in ".@":
+                raise KeyError(ch)
+        rows.append(line)
+    return rows
+
+
+def parse_scen_text(data: bytes, n_agents: int):
+    """(starts, goals) of a .scen file's contents (`utils.py:8-30`): the first line is skipped, every further line is
+    unpacked into exactly nine tab-separated fields (ValueError otherwise), fields 4..7 are `int()`ed and used as
+    (row, col) pairs; reading stops after `n_agents` lines."""
+    text = data.decode("latin-1").replace("\r\n", "\n").replace("\r", "\n")
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    if not lines:
+        raise StopIteration
+    starts, goals = [], []
+    for i, line in enumerate(lines[1:]):
+        fields = line.split("\t")
+        if len(fields) != 9:
+            raise ValueError("expected 9 fields, got %d" % len(fields))
+        starts.append((int(fields[4]), int(fields[5])))
+        goals.append((int(fields[6]), int(fields[7])))
+        if i == n_agents - 1:
+            break
+    return tuple(starts), tuple(goals)
