@@ -236,9 +236,11 @@ def test_group_two_word_states_and_errors():
     with pytest.raises(_native.NativeError) as ei:
         _native.Group([ea, c4], [1, 1])
     assert ei.value.code == _native.MAPF_ERR_UNSUPPORTED
-    berlin = make_engine(_shipped_spec("Berlin_1_256", 1, 4, 0.2, -1000.0, 100.0, -1.0, True))
-    with pytest.raises(_native.NativeError):
-        _native.Group([c4, berlin], [1, 1])
+    c2 = make_engine(_shipped_spec("room-32-32-4", 1, 2, 0.2, -1000.0, 100.0, -1.0, True))
+    berlin = make_engine(_shipped_spec("Berlin_1_256", 1, 2, 0.2, -1000.0, 100.0, -1.0, True))
+    with pytest.raises(_native.NativeError) as ei:
+        _native.Group([c2, berlin], [1, 1])
+    assert ei.value.code == _native.MAPF_ERR_UNSUPPORTED and "shared memory" in ei.value.text
     with pytest.raises(ValueError):
         group.step(states[:10], torch.zeros(10, dtype=torch.int32, device="cuda"))
 
