@@ -63,6 +63,8 @@ struct mapf_ctx {
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
     size_t smem_backup = 0;      // smem_base + per-warp backup slabs
     int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout_tape = 0;
+    int grid_lanes = 0, grid_lanes_tape = 0;
+    LaneConsts lanes;                   // per-lane constants of the lane-per-agent step (k_step_lanes)
     int grid_expand = 0, grid_expand_range = 0, grid_plain = 0, grid_backup = 0, grid_backup_range = 0;
     KernelSet ks;
     u32 pat_triple[MAPF_MAX_PATTERNS];  // merge patterns (see PatternList)
@@ -473,6 +475,27 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         sp.image_bytes = (u32)(image_head + (luts ? lut_pad : 0));
     }
     pick_kernels(n, sp.words, luts, &ctx->ks);
+    memset(&ctx->lanes, 0, sizeof(ctx->lanes));
+    if (ctx->ks.step_lanes_philox) {
+        u128 pw = 1;
+        u32 p5 = 1;
+        for (int i = 0; i < 8; ++i) {
+            if (i < n) {  // L**i < nS < 2**63
+                const FastDiv f = make_fastdiv((u64)pw);
+                ctx->lanes.div_magic[i] = f.magic;
+                ctx->lanes.div_shift[i] = f.shift;
+                ctx->lanes.powL[i] = (u64)pw;
+                pw *= (u128)L;
+            }
+            if (i >= 1) {  // floor(a / 5**i) for a < 2**20: round-up magic with s = 32 + floor(log2 d)
+                const int fl = 31 - __builtin_clz(p5);
+                const u64 two_s = 1ull << (32 + fl);
+                ctx->lanes.act_magic[i] = (u32)((two_s + p5 - 1) / p5);
+                ctx->lanes.act_shift[i] = (u32)fl;
+            }
+            p5 *= 5u;
+        }
+    }
     ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
     ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
     ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
@@ -482,12 +505,14 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
+        {ctx->ks.step_lanes_philox, ctx->smem_base, &ctx->grid_lanes},
+        {ctx->ks.step_lanes_tape, ctx->smem_base, &ctx->grid_lanes_tape},
         {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand},
         {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range},
         {ctx->ks.backup, ctx->smem_backup, &ctx->grid_backup},
         {ctx->ks.backup_range, ctx->smem_backup, &ctx->grid_backup_range}};
     for (auto &pl : plan) {
-        if (!pl.fn) continue;  // two-word states have no backup kernels
+        if (!pl.fn) continue;  // two-word states have no backup kernels; the lane-per-agent step covers 2..8 agents
         if (pl.smem > 48 * 1024)
             CTX_TRY(cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         int rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
@@ -934,6 +959,36 @@ extern "C" int mapf_step(const mapf_ctx *ctx, const void *states, const int32_t 
     DeviceGuard g(ctx->device);
     return launch_step(ctx, states, actions, B, uniforms, seed, step_index, env_offset, options, next_states, reward, prob,
                        done, collision, (cudaStream_t)stream);
+}
+
+extern "C" int mapf_step_lanes(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B,
+                               const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
+                               uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
+                               uint8_t *collision, void *stream) {
+    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done || !collision)))
+        return fail(MAPF_ERR_INVALID, "mapf_step_lanes: bad argument");
+    if (!ctx->ks.step_lanes_philox)
+        return fail(MAPF_ERR_UNSUPPORTED, "the lane-per-agent step covers 2..8 agents, one-word states and move tables staged "
+                                          "in shared memory; use mapf_step");
+    if (B == 0) return MAPF_OK;
+    if (B > MAPF_LAUNCH_MAX_ENVS) return fail(MAPF_ERR_INVALID, "mapf_step_lanes: at most 2**30 envs per call");
+    if (!uniforms && !ctx->philox_ok)
+        return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
+    DeviceGuard g(ctx->device);
+    DevSpec sp = ctx->sp;
+    LaneConsts lc = ctx->lanes;
+    PhiloxKeys keys = make_keys(seed);
+    u32 nb = (u32)B, op = options;
+    u64 st = step_index, e0 = (u64)env_offset;
+    void *args[] = {&sp, &lc, &keys, &states, &actions, &nb, &uniforms, &st, &e0, &op, &next_states, &reward, &prob, &done,
+                    &collision};
+    // one warp steps 32 envs per round
+    const int64_t warps_needed = (B + 31) / 32, per_cta = ctx->threads / 32;
+    int grid = (int)((warps_needed + per_cta - 1) / per_cta);
+    const int gmax = uniforms ? ctx->grid_lanes_tape : ctx->grid_lanes;
+    if (grid > gmax) grid = gmax;
+    LAUNCH(uniforms ? ctx->ks.step_lanes_tape : ctx->ks.step_lanes_philox, grid, ctx->threads, ctx->smem_base, stream, args);
+    return MAPF_OK;
 }
 
 extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32_t *actions, int64_t T, int64_t B,

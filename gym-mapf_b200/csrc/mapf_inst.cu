@@ -14,6 +14,10 @@ static void fill(KernelSet *k) {
     k->step_tape = (const void *)k_step<N, W, LUTS, true, 1>;
     k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false>;
     k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true>;
+    if constexpr (LUTS && W == 1 && N >= 2 && N <= 8) {
+        k->step_lanes_philox = (const void *)k_step_lanes<N, false>;
+        k->step_lanes_tape = (const void *)k_step_lanes<N, true>;
+    }
     if (LUTS) {
         k->step_group_philox = (const void *)k_step_group<N, W, false>;
         k->step_group_tape = (const void *)k_step_group<N, W, true>;

@@ -273,3 +273,59 @@ def test_multimap_vec_env():
             n1, r1, d1, i1 = v.step(acts[lo:hi].contiguous())
             assert torch.equal(n1, ns[lo:hi]) and torch.equal(r1, r[lo:hi]) and torch.equal(d1, d[lo:hi])
             assert torch.equal(i1["prob"], info["prob"][lo:hi]) and torch.equal(i1["collision"], info["collision"][lo:hi])
+
+
+# ---- the lane-per-agent mapping of the step (mapf_step_lanes) --------------------------------------------------------
+@gpu
+@pytest.mark.parametrize("n,map_name,scen", [(2, "empty-8-8", 1), (3, "room-32-32-4", 1), (4, "room-32-32-4", 1),
+                                             (5, "empty-16-16", 2), (6, "maze-32-32-4", 10), (7, "empty-16-16", 4),
+                                             (8, "empty-8-8", 3)])
+@pytest.mark.parametrize("soc", [True, False])
+def test_lane_mapping_matches_oracle_and_thread_mapping(n, map_name, scen, soc):
+    """k_step_lanes (one warp lane per agent, warp-primitive conflict detection) == the C oracle given the uniforms, and
+    == k_step draw for draw in device-sampling mode; ragged batch sizes, conflict-dense states."""
+    import torch
+    from engine_util import make_engine, make_oracle, u64
+    sp = _shipped_spec(map_name, scen, n, 0.2, -1000.0, 100.0, -1.0, soc)
+    eng = make_engine(sp)
+    ora = make_oracle(sp)
+    assert eng.words == 1
+    rng = np.random.default_rng(100 * n + soc)
+    for B in (1, 31, 33, 4099):
+        cells = rng.integers(0, eng.L, (B, n)).astype(np.int32)
+        # conflict-dense half: every agent inside a few cells around agent 0 (vertex and swap clashes, shared cells)
+        near = (cells[:, :1] + rng.integers(0, 3, (B, n))) % eng.L
+        cells[B // 2:] = near[B // 2:]
+        lo, hi = ora.encode(cells)
+        lo[: B // 8] = eng.s0
+        lo[B // 8: B // 6] = eng.goal_state
+        act = rng.integers(0, 5 ** n, B).astype(np.int32)
+        act[::5] = 0   # all STAY: parked agents under SoC
+        uni = rng.random((B, n))
+        states = torch.from_numpy(lo.view(np.int64).copy()).cuda()
+        actions = torch.from_numpy(act).cuda()
+        uniforms = torch.from_numpy(uni).cuda()
+        got = eng.step(states, actions, uniforms=uniforms, mapping="lanes")
+        w = ora.step(lo, hi, act.astype(np.int64), uni)
+        assert np.array_equal(u64(got[0]), w["next_lo"])
+        assert np.array_equal(u64(got[1]), G.f64_to_bits(w["reward"])) and np.array_equal(u64(got[2]), G.f64_to_bits(w["prob"]))
+        assert np.array_equal(got[3].cpu().numpy().astype(np.uint8), w["done"])
+        assert np.array_equal(got[4].cpu().numpy().astype(np.uint8), w["collision"])
+        assert w["collision"].sum() > 0 or B < 31
+        for auto_reset in (False, True):
+            a = eng.step(states, actions, seed=11, step_index=3, env_offset=77, auto_reset=auto_reset)
+            b = eng.step(states, actions, seed=11, step_index=3, env_offset=77, auto_reset=auto_reset, mapping="lanes")
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+
+
+@gpu
+def test_lane_mapping_unsupported():
+    from engine_util import make_engine
+    from gym_mapf_b200 import _native
+    import torch
+    e8 = make_engine(_shipped_spec("room-64-64-8", 1, 8, 0.2, -1000.0, 100.0, -1.0, False))   # two-word states
+    st = e8.states_from_ints([e8.s0])
+    with pytest.raises(_native.NativeError) as ei:
+        e8.step(st, torch.zeros(1, dtype=torch.int32, device="cuda"), mapping="lanes")
+    assert ei.value.code == _native.MAPF_ERR_UNSUPPORTED

@@ -175,6 +175,49 @@ def step_case(tag, env, B, ring):
          steps_per_s=B / t, gbs=by / t / 1e9, frac=by / t / 1e9 / PEAK)
 
 
+def mappings():
+    """The same batched step through (a) the shipped thread-per-env kernel, (b) the lane-per-agent kernel
+    (mapf_step_lanes: __match_any_sync / __shfl_xor_sync / __ballot_sync across an agent group) and (c) the grouped
+    kernel of heterogeneous batches with 1, 4 and 64 specs (mapf_group_step).  Stream launches, ring of buffers > L2."""
+    for map_name, scen, n, B in (("room-32-32-4", 1, 4, 1 << 20), ("empty-32-32", 1, 2, 1 << 20),
+                                 ("room-32-32-4", 13, 6, 1 << 20), ("empty-16-16", 1, 7, 1 << 20)):
+        env = make(map_name, scen, n)
+        eng = env.engine
+        W = eng.words * 8
+        ring = 16
+        g = torch.Generator(device=DEV)
+        g.manual_seed(4)
+        rng = np.random.default_rng(3)
+        states = [random_states(eng, B, rng) for _ in range(ring)]
+        actions = [torch.randint(0, env.nA, (B,), generator=g, device=DEV, dtype=torch.int32) for _ in range(ring)]
+        outs = [(eng.new_states(B), torch.empty(B, dtype=torch.float64, device=DEV),
+                 torch.empty(B, dtype=torch.float64, device=DEV), torch.empty(B, dtype=torch.bool, device=DEV),
+                 torch.empty(B, dtype=torch.bool, device=DEV)) for _ in range(ring)]
+        ref = eng.step(states[0], actions[0], seed=1, step_index=7)
+        by = B * (2 * W + 22)
+        K = ring * 4
+        variants = [("thread-per-env (k_step)", lambda j, i: eng.step(states[j], actions[j], seed=1, step_index=i, out=outs[j])),
+                    ("lane-per-agent (k_step_lanes)",
+                     lambda j, i: eng.step(states[j], actions[j], seed=1, step_index=i, out=outs[j], mapping="lanes"))]
+        for n_specs in (1, 4, 64):
+            # copies of the same spec with different rewards: every CTA re-stages when its tile run crosses a segment
+            envs = [create_mapf_env(map_name, scen, n, 0.2, -1000.0 - k, 100.0, -1.0, OptimizationCriteria.SoC, device=0)
+                    for k in range(n_specs)]
+            grp = _native.Group([e.engine for e in envs], [B // n_specs] * n_specs)
+            variants.append(("grouped, %d specs (k_step_group)" % n_specs,
+                             lambda j, i, grp=grp: grp.step(states[j], actions[j], seed=1, step_index=i, out=outs[j])))
+        for tag, fn in variants:
+            got = fn(0, 7)
+            same = all(torch.equal(a, b) for a, b in zip(got[:1] + got[2:4], ref[:1] + ref[2:4]))  # rewards differ per spec
+
+            def run():
+                for i in range(K):
+                    fn(i % ring, 100 + i)
+            t = timed(run, reps=5, warm=1) / K
+            emit(case="mapping %s n=%d: %s" % (map_name, n, tag), envs=B, us_per_step=t * 1e6, steps_per_s=B / t,
+                 gbs=by / t / 1e9, frac=by / t / 1e9 / PEAK, same_states_probs_dones=bool(same))
+
+
 def c4_step():
     step_case("c4_step room-64-64-8 n=8 Makespan 2**24 envs", make("room-64-64-8", 1, 8, soc=False), 1 << 24, 2)
 
@@ -255,7 +298,7 @@ def backup_case():
                       bit_identical=same))
 
 
-CASES = dict(backup=backup_case, c2_expand=c2_expand, c3_table=c3_table, c4_step=c4_step, c5_sweep=c5_sweep, c2_rollout=c2_rollout,
+CASES = dict(mappings=mappings, backup=backup_case, c2_expand=c2_expand, c3_table=c3_table, c4_step=c4_step, c5_sweep=c5_sweep, c2_rollout=c2_rollout,
              c2_step=c2_step)
 
 if __name__ == "__main__":
