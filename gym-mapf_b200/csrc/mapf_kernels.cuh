@@ -1443,7 +1443,10 @@ k_step_lanes(DevSpec sp, LaneConsts lc, PhiloxKeys keys, const u64 *states, cons
             const u32 fw = active ? __byte_perm(cell, nxt, 0x5410) : 0xffffffffu;      // prev | next << 16
             const u32 bw = active ? __byte_perm(nxt, cell, 0x5410) : 0xfffffffeu;      // next | prev << 16
 #pragma unroll
-            for (int d = 1; d < G; ++d) clash_here = clash_here || (__shfl_xor_sync(0xffffffffu, bw, d) == fw);  // swap
+            for (int d = 1; d < G; ++d) {  // swap: every lane takes part in every shuffle (no short-circuit around it)
+                const u32 other = __shfl_xor_sync(0xffffffffu, bw, d);
+                clash_here = clash_here | (other == fw);
+            }
             const u32 gmask = ((1u << G) - 1u) << gbase;
             const bool dup = (__ballot_sync(0xffffffffu, dup_here) & gmask) != 0u;
             const bool clash = (__ballot_sync(0xffffffffu, clash_here) & gmask) != 0u;
