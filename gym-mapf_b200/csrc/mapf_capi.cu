@@ -1298,12 +1298,12 @@ struct mapf_group {
     int n = 0, words = 0, n_specs = 0;
     int threads = 512, grid = 0;
     int64_t B = 0;
-    u32 n_tiles = 0, spec_off = 0;
+    u32 spec_off = 0;
     size_t smem = 0;
     bool philox_ok = true;
     const void *fn_philox = nullptr, *fn_tape = nullptr;
     DevSpec *d_specs = nullptr;
-    GroupTile *d_tiles = nullptr;
+    u32 *d_seg = nullptr;               // seg_begin[n_specs + 1]
     std::vector<int64_t> seg_begin;
 };
 
@@ -1312,7 +1312,7 @@ extern "C" void mapf_group_destroy(mapf_group *g) {
     {
         DeviceGuard guard(g->device);
         cudaFree(g->d_specs);
-        cudaFree(g->d_tiles);
+        cudaFree(g->d_seg);
     }
     delete g;
 }
@@ -1352,23 +1352,17 @@ extern "C" int mapf_group_create(mapf_ctx *const *ctxs, const int64_t *env_count
     g->spec_off = (u32)((smem_max + 15) & ~(size_t)15);
     g->smem = g->spec_off + ((sizeof(DevSpec) + 15) & ~(size_t)15);
     std::vector<DevSpec> specs(n_specs);
-    std::vector<GroupTile> tiles;
+    std::vector<u32> seg((size_t)n_specs + 1);
     g->seg_begin.resize((size_t)n_specs + 1);
     int64_t at = 0;
     for (int i = 0; i < n_specs; ++i) {
         specs[i] = ctxs[i]->sp;
         g->seg_begin[i] = at;
-        for (int64_t o = 0; o < env_counts[i]; o += GROUP_TILE) {
-            GroupTile t;
-            t.spec = (u32)i; t.begin = (u32)(at + o);
-            t.count = (u32)(env_counts[i] - o < GROUP_TILE ? env_counts[i] - o : GROUP_TILE);
-            t.pad = 0;
-            tiles.push_back(t);
-        }
+        seg[i] = (u32)at;
         at += env_counts[i];
     }
     g->seg_begin[n_specs] = at;
-    g->n_tiles = (u32)tiles.size();
+    seg[n_specs] = (u32)at;
     DeviceGuard guard(g->device);
 #define GRP_TRY(expr)                                                                                  \
     do {                                                                                               \
@@ -1382,9 +1376,8 @@ extern "C" int mapf_group_create(mapf_ctx *const *ctxs, const int64_t *env_count
     if (!g->fn_philox || !g->fn_tape) { mapf_group_destroy(g); return fail(MAPF_ERR_UNSUPPORTED, "no grouped step kernel for this spec"); }
     GRP_TRY(cudaMalloc(&g->d_specs, sizeof(DevSpec) * (size_t)n_specs));
     GRP_TRY(cudaMemcpy(g->d_specs, specs.data(), sizeof(DevSpec) * (size_t)n_specs, cudaMemcpyHostToDevice));
-    GRP_TRY(cudaMalloc(&g->d_tiles, sizeof(GroupTile) * (tiles.size() + 1)));
-    if (!tiles.empty())
-        GRP_TRY(cudaMemcpy(g->d_tiles, tiles.data(), sizeof(GroupTile) * tiles.size(), cudaMemcpyHostToDevice));
+    GRP_TRY(cudaMalloc(&g->d_seg, sizeof(u32) * seg.size()));
+    GRP_TRY(cudaMemcpy(g->d_seg, seg.data(), sizeof(u32) * seg.size(), cudaMemcpyHostToDevice));
     int grid_p = 0, grid_t = 0;
     for (const void *fn : {g->fn_philox, g->fn_tape})
         if (g->smem > 48 * 1024) GRP_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
@@ -1414,12 +1407,14 @@ extern "C" int mapf_group_step(const mapf_group *g, const void *states, const in
     DeviceGuard guard(g->device);
     PhiloxKeys keys = make_keys(seed);
     const DevSpec *specs = g->d_specs;
-    const GroupTile *tiles = g->d_tiles;
-    u32 n_tiles = g->n_tiles, spec_off = g->spec_off, op = options;
+    const u32 *seg = g->d_seg;
+    u32 n_specs = (u32)g->n_specs, nb = (u32)g->B, spec_off = g->spec_off, op = options;
     u64 st = step_index, e0 = (u64)env_offset;
-    void *args[] = {&specs, &tiles, &n_tiles, &spec_off, &keys, &states, &actions, &uniforms, &st, &e0, &op, &next_states,
+    void *args[] = {&specs, &seg, &n_specs, &nb, &spec_off, &keys, &states, &actions, &uniforms, &st, &e0, &op, &next_states,
                     &reward, &prob, &done, &collision};
-    const int grid = (int)(n_tiles < (u32)g->grid ? n_tiles : (u32)g->grid);
+    // every CTA owns a contiguous range of envs; small batches get one CTA per 2 * threads envs
+    const int64_t want = (g->B + 2 * g->threads - 1) / (2 * g->threads);
+    const int grid = (int)(want < g->grid ? want : g->grid);
     LAUNCH(uniforms ? g->fn_tape : g->fn_philox, grid, g->threads, g->smem, stream, args);
     return MAPF_OK;
 }

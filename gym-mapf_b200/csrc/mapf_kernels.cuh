@@ -1231,20 +1231,16 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 // =====================================================================================================
 // Heterogeneous batches: envs of DIFFERENT specs (grid, starts/goals, rewards) in one launch
 // =====================================================================================================
-// The batch is a concatenation of per-spec segments, cut into tiles of at most GROUP_TILE envs.  The tiles are dealt
-// out in contiguous runs, one run per CTA, so a CTA changes spec at most (specs inside its run) times; on a change it
-// re-stages the spec's shared-memory image with one bulk copy (the images of all specs of a group were built for the
+// The batch is a concatenation of per-spec segments (seg_begin[i] .. seg_begin[i + 1] belong to spec i).  Every CTA
+// owns one contiguous, 32-aligned range of envs and walks the segments that overlap it; at a segment change it
+// re-stages that spec's shared-memory image with one bulk copy (the images of all specs of a group were built for the
 // same shared-memory window) and copies the spec's DevSpec behind the largest image, from where the device functions
 // read it instead of the constant bank.  Same agent count, state width and per-env semantics as k_step; the Philox
-// counter is the env's index in the whole batch.
-struct GroupTile {
-    u32 spec, begin, count, pad;
-};
-#define GROUP_TILE 1024
-
+// counter is the env's index in the whole batch.  As in k_step, a thread's next env is loaded, and its slip draws are
+// generated, before the current one is computed.
 template <int N, int WORDS, bool TAPE>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
-k_step_group(const DevSpec *__restrict__ specs, const GroupTile *__restrict__ tiles, u32 n_tiles, u32 spec_off,
+k_step_group(const DevSpec *__restrict__ specs, const u32 *__restrict__ seg_begin, u32 n_specs, u32 B, u32 spec_off,
              PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, const double *__restrict__ uniforms,
              u64 step, u64 env0, u32 opts, u64 *next_states, double *__restrict__ reward, double *__restrict__ prob,
              u8 *__restrict__ done, u8 *__restrict__ coll) {
@@ -1260,17 +1256,28 @@ k_step_group(const DevSpec *__restrict__ specs, const GroupTile *__restrict__ ti
     tb.lut = smem_u32(smem + MAPF_SMEM_LUT);
     tb.act0 = tb.lut;
     tb.lut_g = nullptr;
-    const u32 t0 = (u32)((u64)n_tiles * blockIdx.x / gridDim.x), t1 = (u32)((u64)n_tiles * (blockIdx.x + 1) / gridDim.x);
-    u32 cur = 0xffffffffu, phase = 0;
-    for (u32 t = t0; t < t1; ++t) {
-        const GroupTile tl = tiles[t];
-        if (tl.spec != cur) {
+    const u32 chunks = (B + 31u) >> 5;
+    const u32 r0 = min(B, (u32)((u64)chunks * blockIdx.x / gridDim.x) << 5);
+    const u32 r1 = min(B, (u32)((u64)chunks * (blockIdx.x + 1) / gridDim.x) << 5);
+    // the segment that holds env r0: the last i with seg_begin[i] <= r0
+    u32 s = 0;
+    for (u32 lo_i = 0, hi_i = n_specs; lo_i < hi_i;) {
+        const u32 mid = (lo_i + hi_i + 1) >> 1;
+        if (mid < n_specs && seg_begin[mid] <= r0) { lo_i = mid; s = mid; }
+        else hi_i = mid - 1;
+    }
+    constexpr int NW = ((N + 3) / 4) * 4;
+    u32 phase = 0;
+    for (u32 lo = r0; lo < r1;) {
+        while (seg_begin[s + 1] <= lo) ++s;  // skips empty segments
+        const u32 hi = min(r1, seg_begin[s + 1]);
+        {
             __syncthreads();  // every thread is done with the previous spec's tables (and sees the barrier's init)
-            const u32 *src = reinterpret_cast<const u32 *>(specs + tl.spec);
+            const u32 *src = reinterpret_cast<const u32 *>(specs + s);
             u32 *dst = reinterpret_cast<u32 *>(ssp);
             for (u32 i = threadIdx.x; i < sizeof(DevSpec) / 4; i += blockDim.x) dst[i] = src[i];
             if (threadIdx.x == 0) {
-                const DevSpec &g = specs[tl.spec];
+                const DevSpec &g = specs[s];
                 if (tb.base != g.smem_window) __trap();  // the action table was built for another window address
                 const u32 bytes = g.image_bytes;
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -1283,7 +1290,24 @@ k_step_group(const DevSpec *__restrict__ specs, const GroupTile *__restrict__ ti
                     off += piece;
                 }
             }
-            __syncthreads();  // the DevSpec copy is complete
+        }
+        // the first env of this thread: its inputs and draws are on their way while the image arrives
+        u32 i = lo + threadIdx.x;
+        u64 r_lo = 0, r_hi = 0;
+        u32 r_a = 0;
+        u32 draws[NW];
+        if (i < hi) {
+            load_state<WORDS>(states, i, r_lo, r_hi);
+            r_a = (u32)actions[i];
+            if (!TAPE) {
+                EnvIn<N> tmp;
+                env_draws<N>(keys, env0 + (u64)i, step, tmp);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) draws[j] = tmp.w[j];
+            }
+        }
+        __syncthreads();  // the DevSpec copy is complete
+        {
             u32 ok;
             do {
                 asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -1293,25 +1317,40 @@ k_step_group(const DevSpec *__restrict__ specs, const GroupTile *__restrict__ ti
                              : "memory");
             } while (!ok);
             phase ^= 1u;
-            cur = tl.spec;
         }
         const DevSpec &sp = *ssp;
-        for (u32 i = threadIdx.x; i < tl.count; i += blockDim.x) {
-            const u32 b = tl.begin + i;
+        while (i < hi) {
             EnvIn<N> in;
-            load_state<WORDS>(states, b, in.lo, in.hi);
-            const u32 a = (u32)actions[b];
+            in.lo = r_lo;
+            in.hi = r_hi;
+            const u32 a = r_a;
+            if (!TAPE) {
+#pragma unroll
+                for (int j = 0; j < NW; ++j) in.w[j] = draws[j];
+            }
+            const u32 i_next = i + blockDim.x;
+            if (i_next < hi) {  // in flight during the compute below
+                load_state<WORDS>(states, i_next, r_lo, r_hi);
+                r_a = (u32)actions[i_next];
+            }
             decode_state<N, WORDS, true>(sp, in.lo, in.hi, in.cell);
-            if (!TAPE) env_draws<N>(keys, env0 + (u64)b, step, in);
             load_actions<N>(sp, tb, a, in.actv);
             int nxt[N];
-            const EnvOut o = env_step<N, WORDS, true, TAPE>(sp, tb, in, TAPE ? uniforms + (size_t)b * N : nullptr, opts, nxt);
-            store_state<WORDS>(next_states, b, o.lo, o.hi);
-            reward[b] = o.reward;
-            prob[b] = o.prob;
-            done[b] = (u8)o.done;
-            coll[b] = (u8)o.coll;
+            const EnvOut o = env_step<N, WORDS, true, TAPE>(sp, tb, in, TAPE ? uniforms + (size_t)i * N : nullptr, opts, nxt);
+            store_state<WORDS>(next_states, i, o.lo, o.hi);
+            reward[i] = o.reward;
+            prob[i] = o.prob;
+            done[i] = (u8)o.done;
+            coll[i] = (u8)o.coll;
+            if (!TAPE && i_next < hi) {
+                EnvIn<N> tmp;
+                env_draws<N>(keys, env0 + (u64)i_next, step, tmp);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) draws[j] = tmp.w[j];
+            }
+            i = i_next;
         }
+        lo = hi;
     }
 }
 
