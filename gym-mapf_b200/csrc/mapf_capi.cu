@@ -1415,7 +1415,20 @@ extern "C" int mapf_group_step(const mapf_group *g, const void *states, const in
     // every CTA owns a contiguous range of envs; small batches get one CTA per 2 * threads envs
     const int64_t want = (g->B + 2 * g->threads - 1) / (2 * g->threads);
     const int grid = (int)(want < g->grid ? want : g->grid);
-    LAUNCH(uniforms ? g->fn_tape : g->fn_philox, grid, g->threads, g->smem, stream, args);
+    // programmatic stream serialization (see launch_step): this launch may begin, up to its griddepcontrol.wait, while
+    // the previous kernel of the stream is still draining
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(g->threads);
+    cfg.dynamicSmemBytes = g->smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, uniforms ? g->fn_tape : g->fn_philox, args);
+    if (e != cudaSuccess) return fail(MAPF_ERR_CUDA, "launch k_step_group: %s", cudaGetErrorString(e));
     return MAPF_OK;
 }
 

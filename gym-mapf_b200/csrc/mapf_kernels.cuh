@@ -1245,6 +1245,10 @@ k_step_group(const DevSpec *__restrict__ specs, const u32 *__restrict__ seg_begi
              u64 step, u64 env0, u32 opts, u64 *next_states, double *__restrict__ reward, double *__restrict__ prob,
              u8 *__restrict__ done, u8 *__restrict__ coll) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // Programmatic dependent launch, as in k_step: the next launch of the stream may begin its prologue while this grid
+    // drains, and this grid stages its first spec and generates its first draws before it waits for the previous one.
+    asm volatile("griddepcontrol.launch_dependents;");
+    bool waited = false;
     DevSpec *ssp = reinterpret_cast<DevSpec *>(smem + spec_off);
     const u32 bar = smem_u32(smem + MAPF_SMEM_BAR);
     if (threadIdx.x == 0) {
@@ -1296,15 +1300,19 @@ k_step_group(const DevSpec *__restrict__ specs, const u32 *__restrict__ seg_begi
         u64 r_lo = 0, r_hi = 0;
         u32 r_a = 0;
         u32 draws[NW];
+        if (!TAPE && i < hi) {
+            EnvIn<N> tmp;
+            env_draws<N>(keys, env0 + (u64)i, step, tmp);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) draws[j] = tmp.w[j];
+        }
+        if (!waited) {  // the states may be the previous launch's output: no global load before this point
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            waited = true;
+        }
         if (i < hi) {
             load_state<WORDS>(states, i, r_lo, r_hi);
             r_a = (u32)actions[i];
-            if (!TAPE) {
-                EnvIn<N> tmp;
-                env_draws<N>(keys, env0 + (u64)i, step, tmp);
-#pragma unroll
-                for (int j = 0; j < NW; ++j) draws[j] = tmp.w[j];
-            }
         }
         __syncthreads();  // the DevSpec copy is complete
         {
