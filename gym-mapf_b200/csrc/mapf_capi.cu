@@ -652,8 +652,13 @@ static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, 
     i64 *partial = (i64 *)scratch;
     void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
     LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
-    k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
-    k_scan_final<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr);
+    const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
+    if (chunks <= SCAN_FOLD_MAX_CHUNKS) {  // two launches: every final block adds up the chunk totals before it itself
+        k_scan_final<true><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+    } else {
+        k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        k_scan_final<false><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+    }
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
 }
@@ -693,8 +698,13 @@ extern "C" int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64
     if (chunks > 0x7fffffff) return fail(MAPF_ERR_INVALID, "too many rows for one scan");
     i64 *partial = (i64 *)scratch;
     k_scan_partials<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial);
-    k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
-    k_scan_final<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr);
+    const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
+    if (chunks <= SCAN_FOLD_MAX_CHUNKS) {
+        k_scan_final<true><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+    } else {
+        k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        k_scan_final<false><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+    }
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
 }

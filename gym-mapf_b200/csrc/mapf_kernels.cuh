@@ -264,30 +264,50 @@ static __global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_c
     if (threadIdx.x == 0) partial[n_chunks] = carry;
 }
 
+// Last pass of the scan: row_ptr[i] = sum of in[0 .. i), row_ptr[B] = the total.  A thread owns two consecutive elements
+// in each of four 512-element passes, so every load and store is a fully coalesced 16-byte access (vec_ok: both arrays
+// 16-byte aligned).  FOLD: the chunk's offset is summed here from the raw per-chunk totals (no spine launch); otherwise
+// `partial` has been scanned by k_scan_spine.
+template <bool FOLD>
 static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict__ in, i64 B, const i64 *__restrict__ partial,
-                                                    i64 *__restrict__ row_ptr) {
+                                                           i64 *__restrict__ row_ptr, int vec_ok) {
     __shared__ i64 ws[8];
-    i64 base = (i64)blockIdx.x * SCAN_CHUNK;
-    i64 carry = partial[blockIdx.x];
-    // thread t owns 8 consecutive elements of the chunk
-    i64 v[SCAN_CHUNK / 256];
-    i64 s = 0;
+    const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
+    constexpr int PASSES = SCAN_CHUNK / 512;
+    i64 v0[PASSES], v1[PASSES];
 #pragma unroll
-    for (int j = 0; j < SCAN_CHUNK / 256; ++j) {
-        i64 i = base + (i64)threadIdx.x * (SCAN_CHUNK / 256) + j;
-        v[j] = i < B ? in[i] : 0;
-        s += v[j];
+    for (int p = 0; p < PASSES; ++p) {
+        const i64 i = base + p * 512 + 2 * (i64)threadIdx.x;
+        if (vec_ok && i + 1 < B) {
+            const longlong2 x = *reinterpret_cast<const longlong2 *>(in + i);
+            v0[p] = x.x; v1[p] = x.y;
+        } else {
+            v0[p] = i < B ? in[i] : 0;
+            v1[p] = i + 1 < B ? in[i + 1] : 0;
+        }
     }
-    i64 total;
-    i64 ex = block_scan_256(s, ws, total) + carry;
+    i64 carry;
+    if (FOLD) {
+        i64 s = 0;
+        for (i64 c = threadIdx.x; c < (i64)blockIdx.x; c += 256) s += partial[c];
+        block_scan_256(s, ws, carry);
+    } else {
+        carry = partial[blockIdx.x];
+    }
 #pragma unroll
-    for (int j = 0; j < SCAN_CHUNK / 256; ++j) {
-        i64 i = base + (i64)threadIdx.x * (SCAN_CHUNK / 256) + j;
-        if (i < B) row_ptr[i] = ex;
-        ex += v[j];
+    for (int p = 0; p < PASSES; ++p) {
+        const i64 i = base + p * 512 + 2 * (i64)threadIdx.x;
+        i64 total;
+        const i64 ex = block_scan_256(v0[p] + v1[p], ws, total) + carry;
+        carry += total;
+        if (i < B) {  // row_ptr has B + 1 entries: i + 1 <= B is always in range, and row_ptr[B] = ex + v0 when i + 1 == B
+            if (vec_ok) *reinterpret_cast<longlong2 *>(row_ptr + i) = make_longlong2(ex, ex + v0[p]);
+            else { row_ptr[i] = ex; row_ptr[i + 1] = ex + v0[p]; }
+        }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) row_ptr[B] = partial[gridDim.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) row_ptr[B] = carry;
 }
+#define SCAN_FOLD_MAX_CHUNKS 4096  // up to this many chunks every final block sums the chunk totals before it itself
 
 // Row lengths AND the per-chunk sums of the scan in one pass (saves the scan's first read of row_len and a launch):
 // block b owns rows [b * SCAN_CHUNK, (b + 1) * SCAN_CHUNK).
@@ -298,23 +318,32 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
     __shared__ i64 ws[8];
     const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
     i64 sum = 0;
-#pragma unroll 2
-    for (int j = 0; j < SCAN_CHUNK / 256; ++j) {
-        const i64 b = base + j * 256 + threadIdx.x;
-        if (b < B) {
-            u64 lo, hi;
-            u32 a;
-            row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
+    // two halves of four rows: the four rows' inputs are loaded before the first is decoded (memory-level parallelism)
+#pragma unroll
+    for (int h = 0; h < SCAN_CHUNK / 256; h += 4) {
+        u64 lo[4], hi[4];
+        u32 a[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const i64 b = base + (h + j) * 256 + threadIdx.x;
+            lo[j] = 0; hi[j] = 0; a[j] = 0;
+            if (b < B) row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo[j], hi[j], a[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const i64 b = base + (h + j) * 256 + threadIdx.x;
             int cell[N], act[N];
-            decode_state<N, WORDS>(sp, lo, hi, cell);
-            decode_action<N>(a, act);
+            decode_state<N, WORDS>(sp, lo[j], hi[j], cell);
+            decode_action<N>(a[j], act);
             i64 len = 1;
-            if (!is_terminal<N>(sp, cell, lo, hi)) {
+            if (!is_terminal<N>(sp, cell, lo[j], hi[j])) {
 #pragma unroll
                 for (int i = 0; i < N; ++i) len *= (i64)ENT_K(__ldg(sp.lut + cell[i] * 5 + act[i]));
             }
-            row_len[b] = len;
-            sum += len;
+            if (b < B) {
+                row_len[b] = len;
+                sum += len;
+            }
         }
     }
     i64 total;

@@ -330,3 +330,24 @@ def test_lane_mapping_unsupported():
     with pytest.raises(_native.NativeError) as ei:
         e8.step(st, torch.zeros(1, dtype=torch.int32, device="cuda"), mapping="lanes")
     assert ei.value.code == _native.MAPF_ERR_UNSUPPORTED
+
+
+# ---- exclusive scan of row lengths (mapf_scan_rows): folded and spine paths, aligned and unaligned buffers ------------
+@gpu
+@pytest.mark.parametrize("B", [1, 2, 511, 512, 513, 2047, 2048, 2049, 100001, (4096 * 2048) + 4097])
+def test_scan_rows_matches_cumsum(B):
+    import torch
+    from engine_util import make_engine
+    from gym_mapf_b200._native import _ptr, check, lib
+    eng = make_engine(_shipped_spec("empty-8-8", 1, 2, 0.2, -1000.0, 100.0, -1.0, True))
+    g = torch.Generator(device="cuda").manual_seed(B)
+    for shift in (0, 1):   # shift 1: the arrays start on an odd element, i.e. only 8-byte aligned (scalar path)
+        buf_len = torch.randint(1, 6562, (B + 2,), generator=g, device="cuda", dtype=torch.int64)
+        buf_ptr = torch.full((B + 3,), -7, device="cuda", dtype=torch.int64)
+        row_len, row_ptr = buf_len[shift:shift + B], buf_ptr[shift:shift + B + 1]
+        scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device="cuda")
+        check(lib().mapf_scan_rows(eng._h, row_len.data_ptr(), B, row_ptr.data_ptr(), _ptr(scratch), eng._stream()))
+        want = torch.zeros(B + 1, dtype=torch.int64, device="cuda")
+        want[1:] = torch.cumsum(row_len, 0)
+        assert torch.equal(row_ptr, want)
+        assert int(buf_ptr[shift + B + 1]) == -7 and (shift == 0 or int(buf_ptr[0]) == -7)   # nothing written outside
