@@ -333,6 +333,9 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> step -> D2H, every step
     e2e = None
     if not args.no_e2e:
+        # the pinned buffers are allocated (first-touched) on the GPU's own NUMA node; undone after the leg so that the
+        # cpu_baseline leg sees every host core again
+        prev_affinity = None if os.environ.get("BENCH_NO_NUMA_BIND") else sharding.bind_host_to_device(local)
         hs = torch.empty(eng.state_shape(B), dtype=torch.int64).pin_memory()
         hs.copy_(states[0])
         ha = actions[0].cpu().pin_memory()
@@ -352,7 +355,10 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / float(dt.item()), "unit": "transitions/s",
                "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": B * 26 * world, "steps": n_e2e,
-               "api": "mapf_step_host (C ABI, pinned host buffers in and out)"}
+               "api": "mapf_step_host (C ABI, pinned host buffers in and out)",
+               "host_numa_bind": prev_affinity is not None}
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)
 
     if rank == 0:
         peak, peak_src = load_peaks()

@@ -105,3 +105,28 @@ def sharded_value_iteration(backup_and_greedy, n_states, world, rank, gamma=1.0,
         if float(delta.item()) <= eps:
             break
     return V, policy, it
+
+
+def bind_host_to_device(device_index):
+    """Host-buffer paths (`mapf_step_host`, pinned staging buffers): run the calling process on the CPU cores next to
+    GPU `device_index` (its NUMA node), so that page-locked buffers allocated afterwards are first-touched in the memory
+    the GPU reaches without crossing the socket interconnect.  Returns the previous affinity set (pass it to
+    `os.sched_setaffinity(0, ...)` to undo), or None when the topology cannot be read -- then nothing is changed."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible and visible.replace(",", "").isdigit() else device_index
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        before = os.sched_getaffinity(0)
+        cpus &= before
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return before
+    except Exception:  # noqa: BLE001 - no NVML, no permission, unknown topology: leave the affinity alone
+        return None
