@@ -21,7 +21,7 @@ EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_mov
            "mapf_count_scan_range", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_step_lanes", "mapf_rollout", "mapf_step_host",
            "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_greedy_bcast", "mapf_count_predecessors", "mapf_predecessors",
-           "mapf_projected_words", "mapf_project_states", "mapf_parse_map_text", "mapf_ctx_create_from_text", "mapf_ctx_grid",
+           "mapf_projected_words", "mapf_project_states", "mapf_parse_map_text", "mapf_parse_scen_text", "mapf_ctx_create_from_text", "mapf_ctx_grid",
            "mapf_group_create", "mapf_group_destroy", "mapf_group_size", "mapf_group_step", "mapf_last_error",
            "mapf_version"]
 
@@ -102,6 +102,7 @@ def lib():
         L.mapf_projected_words.argtypes = [vp, i32]
         L.mapf_project_states.argtypes = [vp, vp, i64, vp, i32, vp, vp]
         L.mapf_parse_map_text.argtypes = [C.c_char_p, i64, i32, C.POINTER(i32), C.POINTER(i32), vp, i64]
+        L.mapf_parse_scen_text.argtypes = [C.c_char_p, i64, i32, vp, vp, C.POINTER(i32)]
         L.mapf_ctx_create_from_text.argtypes = [C.c_char_p, i64, C.c_char_p, i64, i32, C.c_double, C.c_double, C.c_double,
                                                 C.c_double, i32, i32, C.POINTER(vp)]
         L.mapf_ctx_grid.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
@@ -464,6 +465,19 @@ def parse_map_text(map_text, device=0):
     out = np.zeros(max(1, len(data)), np.uint8)
     check(lib().mapf_parse_map_text(data, len(data), int(device), C.byref(h), C.byref(w), _ptr(out), out.size))
     return out[:h.value * w.value].reshape(h.value, w.value).copy()
+
+
+def parse_scen_text(scen_text, n_agents):
+    """(starts, goals) of a .scen file's CONTENTS by the library's host parser (mapf_parse_scen_text; reference
+    utils.py:8-30).  Needs no GPU."""
+    data = scen_text.encode("utf8") if isinstance(scen_text, str) else bytes(scen_text)
+    n_agents = int(n_agents)
+    start_rc = np.zeros(2 * max(1, n_agents), np.int32)
+    goal_rc = np.zeros(2 * max(1, n_agents), np.int32)
+    found = C.c_int32()
+    check(lib().mapf_parse_scen_text(data, len(data), n_agents, _ptr(start_rc), _ptr(goal_rc), C.byref(found)))
+    pairs = lambda a: tuple((int(a[2 * i]), int(a[2 * i + 1])) for i in range(found.value))  # noqa: E731
+    return pairs(start_rc), pairs(goal_rc)
 
 
 class Group:

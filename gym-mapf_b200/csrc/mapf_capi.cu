@@ -1210,6 +1210,16 @@ static int parse_scen_text(const char *text, int64_t len, int n_agents, int32_t 
     return MAPF_OK;
 }
 
+extern "C" int mapf_parse_scen_text(const char *scen_text, int64_t scen_len, int32_t n_agents, int32_t *start_rc,
+                                    int32_t *goal_rc, int32_t *n_found) {
+    if (!scen_text || scen_len < 0 || n_agents < 1 || !start_rc || !goal_rc || !n_found)
+        return fail(MAPF_ERR_INVALID, "mapf_parse_scen_text: bad argument");
+    int found = 0;
+    const int rc = parse_scen_text(scen_text, scen_len, n_agents, start_rc, goal_rc, &found);
+    *n_found = found;
+    return rc;
+}
+
 extern "C" int mapf_parse_map_text(const char *map_text, int64_t map_len, int device, int32_t *height, int32_t *width,
                                    uint8_t *obstacles, int64_t obstacles_cap) {
     if (!map_text || map_len < 0 || !height || !width) return fail(MAPF_ERR_INVALID, "mapf_parse_map_text: bad argument");

@@ -217,6 +217,15 @@ int mapf_project_states(const mapf_ctx *ctx, const void *states, int64_t B, cons
 int mapf_parse_map_text(const char *map_text, int64_t map_len, int device, int32_t *height, int32_t *width,
                         uint8_t *obstacles, int64_t obstacles_cap);
 
+/* parse_scen_file (utils.py:8-30) for a file's CONTENTS, on the host (a scenario contributes at most n_agents short
+ * lines): the first line is skipped; every further line must hold exactly nine tab-separated fields (the reference's
+ * tuple unpacking raises ValueError otherwise -> MAPF_ERR_INVALID), fields 4..7 are int()ed and stored AS (row, col) of
+ * the start and the goal; reading stops after n_agents lines or at the end of the text.  start_rc / goal_rc: HOST,
+ * 2*n_agents ints each; *n_found = agents read (the reference truncates n_agents to it, utils.py:123).  No device
+ * is touched. */
+int mapf_parse_scen_text(const char *scen_text, int64_t scen_len, int32_t n_agents, int32_t *start_rc, int32_t *goal_rc,
+                         int32_t *n_found);
+
 /* create_mapf_env for file CONTENTS (utils.py:119-135): the map text goes through mapf_parse_map_text, the scenario
  * text through parse_scen_file's rules (utils.py:8-30: first line skipped, nine tab-separated fields per line, fields
  * 4..7 used as (row, col) of start and goal, the first n_agents lines, n_agents truncated to what the file holds),

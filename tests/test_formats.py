@@ -51,6 +51,23 @@ def test_oracle_parsers_match_reference(case):
     assert len(goals) == ok["n_agents"] and L == ok["L"] and str(s0) == ok["s0"]
 
 
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_library_scen_parser_matches_reference(case):
+    """The C library's host-side .scen parser (no GPU involved) against the reference's parse_scen_file."""
+    from gym_mapf_b200 import _native
+    s = case["scen_text"].encode("latin-1")
+    if case.get("error") == "ValueError":
+        with pytest.raises(_native.NativeError) as ei:
+            _native.parse_scen_text(s, case["n_agents"])
+        assert ei.value.code == _native.MAPF_ERR_INVALID
+        return
+    starts, goals = _native.parse_scen_text(s, case["n_agents"])
+    want = O.parse_scen_text(s, case["n_agents"])
+    assert (starts, goals) == want
+    if "ok" in case:
+        assert [list(x) for x in starts] == case["ok"]["starts"] and [list(x) for x in goals] == case["ok"]["goals"]
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 gpu = pytest.mark.gpu
 
