@@ -243,10 +243,8 @@ def c2_rollout():
 
 
 def backup_case():
-    """Fused Bellman backup (no table written): records consumed per second, beside the table-writing path and the
-    C oracle on all host threads (bounded sample)."""
-    import time
-    from oracle import c_oracle
+    """Fused Bellman backup (no table written): records consumed per second, beside the table-writing path.  (Bit
+    identity with the CPU oracle is a test: tests/test_gpu_parity.py::test_backup_large_vs_oracle.)"""
     for map_name, n in (("empty-32-32", 2), ("empty-16-16", 3)):
         env = make(map_name, 1, n, soc=False)
         eng = env.engine
@@ -277,25 +275,10 @@ def backup_case():
             check(lib().mapf_expand_range(eng._h, C.byref(sb), n_states, _ptr(row_ptr), _ptr(ns), _ptr(prob),
                                           _ptr(reward), _ptr(flags), s))
         t_t = timed(table, reps=3, warm=1)
-        # CPU: the C oracle's backup on all host threads, bounded sample
-        rows = ["".join("@" if v else "." for v in r) for r in env.grid.obstacles]
-        ora = c_oracle.COracle(rows, n, env.agents_goals, 0.2, -1000.0, 100.0, -1.0, False)
-        cores = os.cpu_count() or 1
-        ns_cpu = min(n_states, 40000)
-        st = np.repeat(np.arange(s0, s0 + ns_cpu, dtype=np.uint64), nA)
-        ac = np.tile(np.arange(nA, dtype=np.int64), ns_cpu)
-        Vh = V.cpu().numpy()
-        t0 = time.perf_counter()
-        qh = ora.backup(st, np.zeros_like(st), ac, Vh, 0.95, threads=cores)
-        t_cpu = time.perf_counter() - t0
-        same = bool(np.array_equal(qh.view(np.uint64), Q[:ns_cpu].cpu().numpy().reshape(-1).view(np.uint64)))
-        rec_cpu = int(row_len[:ns_cpu * nA].sum().item())
         emit(case="backup %s n=%d (Makespan), slab of %d states x %d actions" % (map_name, n, n_states, nA),
              rows=B, records=records, mean_row=records / B, ms=dict(backup=t_b * 1e3, greedy=t_g * 1e3, table=t_t * 1e3),
              records_per_s=records / t_b, rows_per_s=B / t_b, table_records_per_s=records / t_t,
-             table_bytes_avoided=records * 25, q_bytes_written=B * 8,
-             cpu=dict(records_per_s=rec_cpu / t_cpu, cores=cores, sample="%d states x %d actions, C oracle" % (ns_cpu, nA),
-                      bit_identical=same))
+             table_bytes_avoided=records * 25, q_bytes_written=B * 8)
 
 
 CASES = dict(mappings=mappings, backup=backup_case, c2_expand=c2_expand, c3_table=c3_table, c4_step=c4_step, c5_sweep=c5_sweep, c2_rollout=c2_rollout,
