@@ -184,7 +184,9 @@ class MultiMapVecEnv:
     in `envs`.  Per-env semantics are those of `VecMapfEnv.step` / `MapfEnv.step` (reference mapf_env.py:237-266).
     State tensors are int64[B] (or int64[B, 2] when every spec needs two words)."""
 
-    def __init__(self, envs, counts, seed=0, auto_reset=True):
+    def __init__(self, envs, counts, seed=0, auto_reset=True, env_offset=0):
+        """`env_offset`: index of this batch's first env in a larger (sharded) batch -- it keys the Philox streams, see
+        `sharding.segment_shard`."""
         import torch
         from .. import _native
         if len(envs) != len(counts) or not envs:
@@ -197,6 +199,7 @@ class MultiMapVecEnv:
             self.offsets.append(self.offsets[-1] + c)
         self.num_envs = self.offsets[-1]
         self.seed, self.auto_reset, self.step_count = int(seed), bool(auto_reset), 0
+        self.env_offset = int(env_offset)
         engines = [e.engine for e in self.envs]
         self.device = engines[0].torch_device
         words = {e.words for e in engines}
@@ -252,7 +255,7 @@ class MultiMapVecEnv:
                 continue
             out = (ns[lo:hi], reward[lo:hi], prob[lo:hi], done[lo:hi], coll[lo:hi])
             part.step(self.states[lo:hi], actions[lo:hi], uniforms=uniforms, seed=self.seed, step_index=self.step_count,
-                      env_offset=lo, auto_reset=self.auto_reset, out=out)
+                      env_offset=self.env_offset + lo, auto_reset=self.auto_reset, out=out)
         self.states = ns
         self.step_count += 1
         return ns, reward, done, {"prob": prob, "collision": coll}

@@ -33,6 +33,23 @@ def env_shard(global_envs, world, rank):
     return split_range(global_envs, world, rank)
 
 
+def segment_shard(counts, world, rank):
+    """Heterogeneous batch (MultiMapVecEnv: counts[i] envs of spec i, concatenated): the contiguous shard of rank
+    `rank` as (Shard, [(spec index, envs of that spec inside the shard), ...]).  `Shard.begin` is the `env_offset` of
+    the rank's MultiMapVecEnv, so the union of the shards draws exactly what one GPU draws for the whole batch."""
+    counts = [int(c) for c in counts]
+    if any(c < 0 for c in counts):
+        raise ValueError("negative env count")
+    sh = split_range(sum(counts), world, rank)
+    parts, at = [], 0
+    for i, c in enumerate(counts):
+        lo, hi = max(at, sh.begin), min(at + c, sh.begin + sh.count)
+        if hi > lo:
+            parts.append((i, hi - lo))
+        at += c
+    return sh, parts
+
+
 def table_shard(s_begin, n_states, world, rank):
     """Table mode: rank owns joint states [begin, begin + count) x all actions of the slab [s_begin, s_begin + n_states)."""
     return split_range(n_states, world, rank, begin=s_begin)

@@ -368,3 +368,31 @@ def test_scan_rows_matches_cumsum(B):
         want[1:] = torch.cumsum(row_len, 0)
         assert torch.equal(row_ptr, want)
         assert int(buf_ptr[shift + B + 1]) == -7 and (shift == 0 or int(buf_ptr[0]) == -7)   # nothing written outside
+
+
+@gpu
+def test_multimap_shards_equal_the_whole_batch():
+    """A heterogeneous batch cut into rank shards (sharding.segment_shard) steps exactly like the whole batch: the Philox
+    stream is keyed by the env's index in the global batch."""
+    import torch
+    from gym_mapf_b200 import sharding
+    from gym_mapf_b200.envs.mapf_env import OptimizationCriteria
+    from gym_mapf_b200.envs.utils import create_mapf_env
+    from gym_mapf_b200.envs.vec_env import MultiMapVecEnv
+    envs = [create_mapf_env("room-32-32-4", 1, 4, 0.2, -1000.0, 100.0, -1.0, OptimizationCriteria.SoC),
+            create_mapf_env("maze-32-32-4", 10, 4, 0.3, -10.0, 5.0, -0.5, OptimizationCriteria.Makespan),
+            create_mapf_env("empty-32-32", 2, 4, 0.2, -1000.0, 100.0, -1.0, OptimizationCriteria.SoC)]
+    counts = [700, 45, 1303]
+    whole = MultiMapVecEnv(envs, counts, seed=5)
+    g = torch.Generator(device="cpu").manual_seed(2)
+    acts = [torch.randint(0, 625, (sum(counts),), generator=g, dtype=torch.int32).cuda() for _ in range(4)]
+    ref = [tuple(t.clone() for t in (lambda o: (o[0], o[1], o[2], o[3]["prob"], o[3]["collision"]))(whole.step(a))) for a in acts]
+    for world in (2, 3):
+        for rank in range(world):
+            sh, parts = sharding.segment_shard(counts, world, rank)
+            mm = MultiMapVecEnv([envs[i] for i, _ in parts], [c for _, c in parts], seed=5, env_offset=sh.begin)
+            for a, want in zip(acts, ref):
+                ns, r, d, info = mm.step(a[sh.begin:sh.begin + sh.count].contiguous())
+                got = (ns, r, d, info["prob"], info["collision"])
+                for x, y in zip(got, want):
+                    assert torch.equal(x, y[sh.begin:sh.begin + sh.count])

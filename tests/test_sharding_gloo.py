@@ -181,3 +181,31 @@ def test_sharded_value_iteration_equals_single_rank():
         assert p.exitcode == 0
     iters, it1, same, v0 = q.get()
     assert iters == it1 and same and v0 > 0
+
+
+def test_segment_shard_covers_the_heterogeneous_batch():
+    """sharding.segment_shard: the shards of a concatenation of per-spec segments are disjoint, ordered and complete,
+    for even and uneven splits, empty segments and more ranks than envs."""
+    from gym_mapf_b200 import sharding
+    for counts in ([3000, 1, 2049, 0, 777], [5], [0, 0, 7], [1, 1, 1], [10, 0, 0, 10]):
+        total = sum(counts)
+        for world in (1, 2, 3, 8, 16):
+            seen = []
+            at = 0
+            for rank in range(world):
+                sh, parts = sharding.segment_shard(counts, world, rank)
+                assert sh.begin == at and sum(c for _, c in parts) == sh.count
+                assert [i for i, _ in parts] == sorted({i for i, _ in parts})     # specs in order, each once
+                at += sh.count
+                pos = sh.begin
+                for i, c in parts:
+                    seg_lo = sum(counts[:i])
+                    assert seg_lo <= pos and pos + c <= seg_lo + counts[i] and c > 0
+                    seen.append((i, pos - seg_lo, c))
+                    pos += c
+            assert at == total
+            per_spec = {}
+            for i, off, c in seen:
+                assert per_spec.get(i, 0) == off          # consecutive pieces of a segment
+                per_spec[i] = off + c
+            assert all(per_spec.get(i, 0) == c for i, c in enumerate(counts))
