@@ -307,7 +307,8 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) row_ptr[B] = carry;
 }
-#define SCAN_FOLD_MAX_CHUNKS 4096  // up to this many chunks every final block sums the chunk totals before it itself
+#define SCAN_FOLD_MAX_CHUNKS 2048  // up to this many chunks every final block sums the chunk totals before it itself (the
+                                   // reads grow with the square of the chunk count: beyond ~2500 the spine launch is cheaper)
 
 // Row lengths AND the per-chunk sums of the scan in one pass (saves the scan's first read of row_len and a launch):
 // block b owns rows [b * SCAN_CHUNK, (b + 1) * SCAN_CHUNK).
