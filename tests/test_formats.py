@@ -396,3 +396,79 @@ def test_multimap_shards_equal_the_whole_batch():
                 got = (ns, r, d, info["prob"], info["collision"])
                 for x, y in zip(got, want):
                     assert torch.equal(x, y[sh.begin:sh.begin + sh.count])
+
+
+@gpu
+@pytest.mark.timeout(300)
+def test_fuzz_group_and_lane_kernels_every_agent_count():
+    """Random small grids (obstacles, coinciding starts/goals, every noise level), 1..13 agents: groups of 2-4 random
+    specs per agent count stepped in one launch must equal the C oracle per spec; with 2..8 agents and one-word states
+    the lane-per-agent kernel must as well."""
+    import torch
+    from engine_util import make_engine, make_oracle, u64
+    from gym_mapf_b200 import _native
+    rng = np.random.default_rng(4711)
+
+    def random_spec(n, H, W):
+        while True:
+            grid = rng.random((H, W)) < rng.choice([0.0, 0.15, 0.35])
+            if (~grid).sum() >= 2:
+                break
+        free = [(r, c) for r in range(H) for c in range(W) if not grid[r, c]]
+        pick = lambda: [list(free[int(rng.integers(0, len(free)))]) for _ in range(n)]  # noqa: E731
+        return dict(rows=["".join("@" if v else "." for v in row) for row in grid], n_agents=n, starts=pick(), goals=pick(),
+                    fail_prob=float(rng.choice([0.0, 0.1, 0.2, 0.37, 1.0])), r_clash=float(rng.choice([-1000.0, -3.5])),
+                    r_goal=float(rng.choice([100.0, 7.25])), r_living=float(rng.choice([-1.0, -0.25, 0.0])),
+                    soc=bool(rng.integers(0, 2)))
+
+    for n in range(1, 14):
+        for words in (1, 2):
+            # grid sizes that give one-word (L**n < 2**63) or two-word states for this agent count
+            specs = []
+            for _ in range(40):
+                H, W = (int(rng.integers(2, 7)), int(rng.integers(2, 7))) if words == 1 else (8, int(rng.integers(7, 9)))
+                sp = random_spec(n, H, W)
+                L = sum(row.count(".") for row in sp["rows"])
+                if (L ** n < 2 ** 63) == (words == 1) and L ** n < 2 ** 127:
+                    specs.append(sp)
+                if len(specs) == 3:
+                    break
+            if len(specs) < 2:
+                continue
+            engines = [make_engine(sp) for sp in specs]
+            assert all(e.words == words for e in engines)
+            counts = [int(rng.integers(1, 700)) for _ in specs]
+            group = _native.Group(engines, counts)
+            B = sum(counts)
+            lo, hi = np.zeros(B, np.uint64), np.zeros(B, np.uint64)
+            act = rng.integers(0, 5 ** n, B).astype(np.int32)
+            uni = rng.random((B, n))
+            at = 0
+            for sp, eng, c in zip(specs, engines, counts):
+                cells = rng.integers(0, eng.L, (c, n)).astype(np.int32)
+                lo[at:at + c], hi[at:at + c] = make_oracle(sp).encode(cells)
+                at += c
+            arr = lo.view(np.int64).copy() if words == 1 else np.stack([lo, hi], 1).view(np.int64).copy()
+            states = torch.from_numpy(arr).cuda()
+            actions, uniforms = torch.from_numpy(act).cuda(), torch.from_numpy(uni).cuda()
+            out = group.step(states, actions, uniforms=uniforms)
+            ns = out[0].cpu().numpy().view(np.uint64).reshape(B, -1)
+            at = 0
+            for sp, eng, c in zip(specs, engines, counts):
+                sl = slice(at, at + c)
+                w = make_oracle(sp).step(lo[sl], hi[sl], act[sl].astype(np.int64), uni[sl])
+                assert np.array_equal(ns[sl, 0], w["next_lo"]), (n, words, sp)
+                if words == 2:
+                    assert np.array_equal(ns[sl, 1], w["next_hi"]), (n, words, sp)
+                assert np.array_equal(u64(out[1][sl]), G.f64_to_bits(w["reward"])), (n, words, sp)
+                assert np.array_equal(u64(out[2][sl]), G.f64_to_bits(w["prob"])), (n, words, sp)
+                assert np.array_equal(out[3][sl].cpu().numpy().astype(np.uint8), w["done"])
+                assert np.array_equal(out[4][sl].cpu().numpy().astype(np.uint8), w["collision"])
+                if words == 1 and 2 <= n <= 8:
+                    one = eng.step(states[sl].clone(), actions[sl].clone(), uniforms=uniforms[sl].clone(), mapping="lanes")
+                    for x, y in zip(one, out):
+                        assert torch.equal(x, y[sl]), (n, sp)
+                at += c
+            group.close()
+            for e in engines:
+                e.close()
