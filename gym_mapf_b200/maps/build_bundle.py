@@ -3,7 +3,7 @@
 
 Run once in the build container (the reference tree is not available on the GPU box):
 
-    python gym-mapf_b200/maps/build_bundle.py [/root/reference/gym_mapf/maps]
+    python gym_mapf_b200/maps/build_bundle.py [/root/reference/gym_mapf/maps]
 
 Bundle layout (numpy `.npz`, deflate):
     names                      unicode array of map names

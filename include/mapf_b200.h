@@ -3,7 +3,7 @@
  * The reference (LevyvoNet/gym-mapf) is pure Python and has no FFI: its boundary for this path is the Python
  * API of `MapfEnv` (gym_mapf/envs/mapf_env.py).  Each entry point below states the reference interface it
  * replaces as file:line relative to /root/reference/gym_mapf/envs/.  The Python package `gym_mapf_b200`
- * (gym-mapf_b200/) binds this library with ctypes (gym-mapf_b200/_native.py); INTEGRATION.md shows the stub a
+ * (gym_mapf_b200/) binds this library with ctypes (gym_mapf_b200/_native.py); INTEGRATION.md shows the stub a
  * maintainer of the reference would add.
  *
  * Conventions

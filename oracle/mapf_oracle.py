@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- pure-Python CPU restatement of gym-mapf's joint-transition path.
 
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may import
-this module, and only as the checker.  Nothing under `gym-mapf_b200/` imports it.
+this module, and only as the checker.  Nothing under `gym_mapf_b200/` imports it.
 
 Parity status: PINNED.  `tests/test_oracle_golden.py` checks every function below against fixtures in
 `tests/golden/` that `oracle/make_golden.py` produced by running the *unmodified* reference

@@ -54,7 +54,7 @@ def test_no_cpu_fallback():
 
 
 def test_product_does_not_import_the_oracle():
-    pkg = os.path.join(ROOT, "gym-mapf_b200")
+    pkg = os.path.join(ROOT, "gym_mapf_b200")
     for base, _dirs, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
