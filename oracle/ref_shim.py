@@ -1,8 +1,10 @@
 """TEST INFRASTRUCTURE ONLY -- loader for the *unmodified* reference (`/root/reference/gym_mapf`).
 
-Only `oracle/make_golden.py` and `tests/test_oracle_vs_reference.py` use this file, and only in the build
-container: `/root/reference` does not exist on the GPU box, so nothing in the `-m gpu` tests, `smoke()` or
-`bench.py` may import it.
+Used by `oracle/make_golden*.py`, `tests/test_oracle_vs_reference.py` (skipped when no reference is present) and
+`bench.py --impl reference` (the CPU arm times the unmodified reference when a copy is present).  The reference is
+looked for at `$MAPF_REFERENCE_ROOT`, `/root/reference` (build container only) and `<repo>/baseline/_ref` (the
+offline `pip install --no-deps --target baseline/_ref` of the unmodified reference: git-ignored, shipped to the GPU
+box by gpurun).  Nothing in the `-m gpu` tests or `smoke()` reads `/root/reference`.
 
 The reference imports five third-party names that are not installed here (no network):
 
@@ -13,17 +15,33 @@ The reference imports five third-party names that are not installed here (no net
 
 `install_stubs()` registers minimal stand-ins in `sys.modules`.  `categorical_sample` restates the published
 gym 0.13.0 behaviour (`requirements.txt:7` pins gym==0.13.0): `(np.cumsum(p) > rng.rand()).argmax()`.
-The seeding stub returns a `RandomState(seed)`; the reference's tests never pin that stream (every `step()`
-test uses `fail_prob=0`), so sampling parity is only ever checked through *explicit uniforms* (see
-`UniformTape`), never through the stream itself.
+`np_random` restates gym 0.13.0's `seeding.np_random`: a `RandomState` seeded with the 32-bit words of the first
+8 bytes of sha512(str(seed)) -- the same stream the product's `envs/mapf_env.py:_gym_np_random` builds
+(`tests/test_oracle_golden.py::test_np_random_stream_pinned` pins both).  The reference's own tests never pin that
+stream (every `step()` test uses `fail_prob=0`); step traces are additionally checked through *explicit uniforms*
+(see `UniformTape`).
 """
+import hashlib
 import os
+import struct
 import sys
 import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MAPF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference_root():
+    cands = [os.environ.get("MAPF_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "gym_mapf", "envs")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 class UniformTape:
@@ -47,7 +65,17 @@ def _categorical_sample(prob_n, np_random):
 
 
 def _np_random(seed=None):
-    return np.random.RandomState(seed), seed
+    """gym 0.13.0 `seeding.np_random` (create_seed -> hash_seed -> _bigint_from_bytes -> _int_list_from_bigint)."""
+    seed = int(seed) % 2 ** 64
+    digest = hashlib.sha512(str(seed).encode("utf8")).digest()[:8] + b"\0" * 4  # gym pads to a multiple of 4 + 4
+    big = sum(2 ** (32 * i) * v for i, v in enumerate(struct.unpack("3I", digest)))
+    words = []
+    while big > 0:
+        big, mod = divmod(big, 2 ** 32)
+        words.append(mod)
+    rng = np.random.RandomState()
+    rng.seed(words if words else [0])
+    return rng, seed
 
 
 def install_stubs():

@@ -191,3 +191,19 @@ def test_oracle_projection(name):
             G.big(d["proj_lo_%d" % k][3], d["proj_hi_%d" % k][3])
         k += 1
     assert k >= 5
+
+
+def test_np_random_stream_pinned():
+    """`MapfEnv.np_random` (gym 0.13.0 `seeding.np_random(42)`, mapf_env.py:40,139): the product's restatement and the
+    reference shim's build the same RandomState; the first draws are pinned as bit patterns."""
+    from gym_mapf_b200.envs.mapf_env import GYM_MAPF_SEED, _gym_np_random
+    from oracle import ref_shim
+    a, seed_a = _gym_np_random(GYM_MAPF_SEED)
+    b, seed_b = ref_shim._np_random(GYM_MAPF_SEED)
+    assert GYM_MAPF_SEED == 42 and seed_a == seed_b == 42
+    xa = [a.rand() for _ in range(4)]
+    xb = [b.rand() for _ in range(4)]
+    assert xa == xb
+    assert [v.hex() for v in xa] == ["0x1.7f1f7113f5ff8p-2", "0x1.eff671fe363dcp-2", "0x1.d76f45e56b83cp-1",
+                                     "0x1.ed831da02bffcp-2"]
+    assert np.array_equal(a.get_state()[1], b.get_state()[1])
