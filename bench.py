@@ -5,15 +5,23 @@ Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): room-32-32-4 scen 1, 4 a
 batched step over 2**20 parallel envs PER GPU (weak scaling; shards are independent, no data-path collective).
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm
-    python bench.py --impl reference [--steps K] [--warmup W]           # the reference's CPU path (oracle port)
+    python bench.py --impl reference [--steps K] [--warmup W]           # the reference's own CPU path on the host cores
 
 A "step" = one launch of the step kernel over this rank's 2**20 envs: it reads 8 B state + 4 B action and writes
 8 B next state + 8 B reward + 8 B probability + 1 B done + 1 B collision per env (38 B), drawing the
 slip uniforms on the device (Philox4x32-10).  Steps cycle over a ring of pre-filled (state, action, output) slots
 whose total footprint (>= 8x the 126 MB L2) keeps every timed launch reading from and writing to HBM.
+
+Besides the headline the line carries `other_configs`: every other BASELINE.json config (C1 full table + 10k steps,
+C2 expand / rollout / strong scaling, C3 table slab per rank, C4 2**24-env 128-bit step, C5 agent-count and
+conflict-density sweeps, the maps whose move table does not fit shared memory), each with its fraction of the HBM
+roofline and a `parity` flag: a sample of what the GPU produced, compared bit for bit with the CPU oracle outside the
+timed region.  The headline's own last launch is checked the same way (`parity`).
 """
 import argparse
+import datetime
 import json
+import math
 import os
 import subprocess
 import sys
@@ -30,6 +38,7 @@ STEP_BYTES = 38           # 2W + 22 with W = 8
 RING_SLOTS = 32           # 32 x (12 MB in + 26 MB out) = 1.2 GB >> 126 MB L2
 NCU_DRAM_BYTES_PER_ENV = (100711936 + 162370048) / (1 << 23)   # profiles/r01_h_step_8m_raw.csv
 METRIC = "joint transitions/sec"
+MAX_REPS = 20000
 
 
 def load_peaks():
@@ -92,15 +101,139 @@ def make_env(device=None):
                            device=device)
 
 
-def oracle_env(env):
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py touches oracle/): the cpu_baseline / --impl reference timings, and the
+# oracle as the CHECKER of GPU output samples (never as the thing measured on our arm)
+# ------------------------------------------------------------------------------------------------------------
+def oracle_of(spec):
     from oracle import c_oracle
-    rows = ["".join("@" if v else "." for v in r) for r in env.grid.obstacles]
-    return c_oracle.COracle(rows, env.n_agents, env.agents_goals, FAIL_PROB, R_CLASH, R_GOAL, R_LIVING, True)
+    return c_oracle.COracle(spec["rows"], spec["n_agents"], spec["goals"], spec["fail_prob"], spec["r_clash"],
+                            spec["r_goal"], spec["r_living"], spec["soc"])
 
 
-# ------------------------------------------------------------------------------------------------------------
-# CPU legs (the only places bench.py touches oracle/)
-# ------------------------------------------------------------------------------------------------------------
+def oracle_env(env):
+    return oracle_of({"rows": ["".join("@" if v else "." for v in r) for r in env.grid.obstacles],
+                      "n_agents": env.n_agents, "goals": env.agents_goals, "fail_prob": FAIL_PROB, "r_clash": R_CLASH,
+                      "r_goal": R_GOAL, "r_living": R_LIVING, "soc": True})
+
+
+def philox4x32_10(ctr, key):
+    """numpy Philox4x32-10 (Salmon et al., SC'11): the device-side sampling stream, regenerated on the host so that the
+    oracle can replay a Philox-mode launch.  ctr: four uint64 arrays holding 32-bit words; key: two 32-bit ints."""
+    import numpy as np
+    c = [np.asarray(x, dtype=np.uint64) for x in ctr]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(0xD2511F53) * c[0]
+        p1 = np.uint64(0xCD9E8D57) * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & m32, p1 >> np.uint64(32), p1 & m32
+        c = [(hi1 ^ c[1] ^ k0) & m32, lo1, (hi0 ^ c[3] ^ k1) & m32, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & m32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & m32
+    return c
+
+
+def philox_block(env_ids, step_index, block, seed):
+    import numpy as np
+    n = len(env_ids)
+    return philox4x32_10([env_ids & np.uint64(0xFFFFFFFF), env_ids >> np.uint64(32),
+                          np.full(n, step_index & 0xFFFFFFFF, np.uint64),
+                          np.full(n, (((step_index >> 32) << 8) | block) & 0xFFFFFFFF, np.uint64)],
+                         [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+
+
+def device_uniforms(env_ids, step_index, seed, n_agents):
+    """Agent i's uniform = word i % 4 of block i // 4 at counter (env, step), times 2**-32 (mapf_device.cuh)."""
+    import numpy as np
+    u = np.zeros((len(env_ids), n_agents))
+    for blk in range((n_agents + 3) // 4):
+        words = philox_block(env_ids, step_index, blk, seed)
+        for q in range(4):
+            if blk * 4 + q < n_agents:
+                u[:, blk * 4 + q] = words[q].astype(np.float64) * 2.0 ** -32
+    return u
+
+
+def verify_payload(p):
+    """-> (ok, description).  The CPU oracle recomputes the sample; every field is compared bit for bit."""
+    import numpy as np
+    M64 = (1 << 64) - 1
+    threads = os.cpu_count() or 1
+    kind = p["kind"]
+    if kind == "rows":
+        ora = oracle_of(p["spec"])
+        want = ora.rows(p["s_lo"], p["s_hi"], p["action"], threads=threads)
+        ok = (np.array_equal(want["row_ptr"], p["row_ptr"]) and np.array_equal(want["next_lo"], p["next_lo"])
+              and np.array_equal(want["next_hi"], p["next_hi"])
+              and np.array_equal(want["prob"].view(np.uint64), p["prob"].view(np.uint64))
+              and np.array_equal(want["reward"].view(np.uint64), p["reward"].view(np.uint64))
+              and np.array_equal(want["done"] | (want["collision"] << 1), p["flags"]))
+        return bool(ok), "%d rows / %d records vs the C oracle" % (len(p["action"]), len(p["prob"]))
+    if kind == "table":
+        ora = oracle_of(p["spec"])
+        want = ora.table_checksums(p["s_begin"], p["n_states"])
+        got = dict(zip(want.keys(), p["words"]))
+        return want == got, "8 checksum words of %d states x all actions (%d records) vs the C oracle's table walk" % (
+            p["n_states"], want["count"])
+    if kind == "step":
+        ora = oracle_of(p["spec"])
+        n = p["spec"]["n_agents"]
+        env_ids = np.arange(len(p["action"]), dtype=np.uint64) + np.uint64(p["env_offset"])
+        u = device_uniforms(env_ids, p["step_index"], p["seed"], n)
+        want = ora.step(p["s_lo"], p["s_hi"], p["action"], u, threads=threads)
+        lo, hi = want["next_lo"], want["next_hi"]
+        if p["auto_reset"]:
+            lo = np.where(want["done"] == 1, np.uint64(p["s0"] & M64), lo)
+            hi = np.where(want["done"] == 1, np.uint64(p["s0"] >> 64), hi)
+        ok = (np.array_equal(lo, p["next_lo"]) and np.array_equal(hi, p["next_hi"])
+              and np.array_equal(want["reward"].view(np.uint64), p["reward"].view(np.uint64))
+              and np.array_equal(want["prob"].view(np.uint64), p["prob"].view(np.uint64))
+              and np.array_equal(want["done"], p["done"]) and np.array_equal(want["collision"], p["collision"]))
+        return bool(ok), "%d env-steps (device Philox draws regenerated on the host) vs the C oracle; %d done, %d collisions" % (
+            len(p["action"]), int(want["done"].sum()), int(want["collision"].sum()))
+    if kind == "rollout":
+        ora = oracle_of(p["spec"])
+        n, T = p["spec"]["n_agents"], p["T"]
+        lo, hi = p["s_lo"].copy(), p["s_hi"].copy()
+        env_ids = np.arange(len(lo), dtype=np.uint64) + np.uint64(p["env_offset"])
+        ok = True
+        for t in range(T):
+            stp = p["step_index"] + t
+            w = philox_block(env_ids, stp, 15, p["seed"])
+            frac = (w[0] << np.uint64(32)) | w[1]
+            act = np.array([(int(f) * p["nA"]) >> 64 for f in frac], dtype=np.int64)  # umul64hi(frac, nA)
+            u = device_uniforms(env_ids, stp, p["seed"], n)
+            want = ora.step(lo, hi, act, u, threads=threads)
+            nlo = np.where(want["done"] == 1, np.uint64(p["s0"] & M64), want["next_lo"])
+            nhi = np.where(want["done"] == 1, np.uint64(p["s0"] >> 64), want["next_hi"])
+            ok = ok and (np.array_equal(nlo, p["next_lo"][t]) and np.array_equal(nhi, p["next_hi"][t])
+                         and np.array_equal(want["reward"].view(np.uint64), p["reward"][t].view(np.uint64))
+                         and np.array_equal(want["prob"].view(np.uint64), p["prob"][t].view(np.uint64))
+                         and np.array_equal(want["done"], p["done"][t]) and np.array_equal(want["collision"], p["collision"][t]))
+            lo, hi = nlo, nhi
+        return bool(ok), "%d envs x %d steps (device-drawn actions and slips regenerated on the host) vs the C oracle" % (len(lo), T)
+    if kind == "c1":
+        from gym_mapf_b200.envs.mapf_env import GYM_MAPF_SEED, _gym_np_random
+        from oracle import mapf_oracle
+        ora = oracle_of(p["spec"])
+        want = ora.table_checksums(0, p["nS"])
+        ok = want == dict(zip(want.keys(), p["words"])) and want["count"] == 669808 == p["scalar_transitions"]
+        sp = p["spec"]
+        spec = mapf_oracle.OracleSpec(sp["rows"], sp["n_agents"], sp["starts"], sp["goals"], sp["fail_prob"], sp["r_clash"],
+                                      sp["r_goal"], sp["r_living"], sp["soc"])
+        twin, _ = _gym_np_random(GYM_MAPF_SEED)  # the stream env.step() consumed
+        for i, a in enumerate(p["acts"]):
+            s = p["trace_s"][i]
+            term = spec.is_terminal(mapf_oracle.to_digits(s, spec.L, spec.n))
+            u = [] if term else [twin.rand() for _ in range(spec.n)]
+            ns, r, done, prob, _, _ = spec.step(s, int(a), u)
+            ok = ok and ns == p["trace_ns"][i] and float(r) == float(p["trace_r"][i]) and bool(done) == bool(p["trace_d"][i]) \
+                and float(prob) == float(p["trace_p"][i])
+        return bool(ok), "all 669 808 records by checksum vs the C oracle + 10 000 scalar env.step() calls vs the Python oracle"
+    return False, "unknown payload kind %r" % kind
+
+
 def cpu_c_port(env, seconds=4.0):
     """C oracle, all host threads, on the bench batch (2**20 envs at the start state, random actions/uniforms)."""
     import numpy as np
@@ -122,16 +255,43 @@ def cpu_c_port(env, seconds=4.0):
     return B * reps / dt, cores, "%d x 2**20-env batches, C port of the reference, %d threads" % (reps, cores)
 
 
+_WORKER = {}
+
+
 def _py_worker(args):
-    seconds, seed = args
+    """One host process stepping ONE env sequentially for `seconds` (random policy, reset on done).  kind "reference":
+    the unmodified reference's MapfEnv.step (mapf_env.py:237-266); kind "port": oracle/mapf_oracle.py."""
+    seconds, seed, kind = args
     import numpy as np
-    from oracle import mapf_oracle
-    env = make_env()
-    rows = ["".join("@" if v else "." for v in r) for r in env.grid.obstacles]
-    spec = mapf_oracle.OracleSpec(rows, env.n_agents, env.agents_starts, env.agents_goals, FAIL_PROB, R_CLASH, R_GOAL,
-                                  R_LIVING, True)
     rng = np.random.default_rng(seed)
-    s, n = spec.s0, 0
+    n = 0
+    if kind == "reference":
+        if "ref_env" not in _WORKER:
+            from oracle import ref_shim
+            ref_shim.load_reference()
+            import gym_mapf.envs.mapf_env as me
+            import gym_mapf.envs.utils as ut
+            _WORKER["ref_env"] = ut.create_mapf_env(MAP, SCEN, N_AGENTS, FAIL_PROB, R_CLASH, R_GOAL, R_LIVING,
+                                                    me.OptimizationCriteria.SoC)
+        env = _WORKER["ref_env"]
+        env.reset()
+        nA = env.nA
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for _ in range(100):
+                _, _, done, _ = env.step(int(rng.integers(0, nA)))
+                if done:
+                    env.reset()
+            n += 100
+        return n, time.perf_counter() - t0
+    if "spec" not in _WORKER:
+        from oracle import mapf_oracle
+        env = make_env()
+        rows = ["".join("@" if v else "." for v in r) for r in env.grid.obstacles]
+        _WORKER["spec"] = mapf_oracle.OracleSpec(rows, env.n_agents, env.agents_starts, env.agents_goals, FAIL_PROB,
+                                                 R_CLASH, R_GOAL, R_LIVING, True)
+    spec = _WORKER["spec"]
+    s = spec.s0
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         for _ in range(200):
@@ -142,30 +302,27 @@ def _py_worker(args):
     return n, time.perf_counter() - t0
 
 
-def cpu_python_port(seconds=4.0, pool=None):
-    """Pure-Python port (the reference itself is pure Python), one process per host core."""
-    import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    own = pool is None
-    if own:
-        pool = mp.get_context("spawn").Pool(cores)
-    try:
-        res = pool.map(_py_worker, [(seconds, 100 + i) for i in range(cores)])
-    finally:
-        if own:
-            pool.close()
-            pool.join()
+def reference_kind():
+    from oracle import ref_shim
+    return "reference" if ref_shim.reference_available() else "port"
+
+
+def cpu_python(seconds, pool, kind, cores):
+    res = pool.map(_py_worker, [(seconds, 100 + i, kind) for i in range(cores)])
     total = sum(r[0] for r in res)
     dt = max(r[1] for r in res)
-    return total / dt, cores, "%d sequential env-steps in %d processes, pure-Python port, %.2f s window" % (
-        total, cores, seconds)
+    what = ("the UNMODIFIED reference's MapfEnv.step (mapf_env.py:237-266, imported through oracle/ref_shim.py)"
+            if kind == "reference" else "pure-Python port oracle/mapf_oracle.py (no copy of the reference present)")
+    return total / dt, "%d sequential env-steps in %d processes (one env each, random policy, reset on done), %s, %.2f s window" % (
+        total, cores, what, seconds)
 
 
 def run_reference(args):
-    """The reference's own CPU implementation of the path on the host cores.  gym-mapf is pure Python (nothing to
-    compile into oracle/_ref), so this times the pure-Python port (oracle/mapf_oracle.py, pinned to the reference by
-    tests/golden) with one process per core; a step = one bounded window of sequential env-steps in every process,
-    sized so that the whole run stays within about two minutes."""
+    """The reference's own CPU implementation of the path on the host cores: gym-mapf is single-threaded pure Python,
+    so one process per core each steps its own env through the UNMODIFIED `MapfEnv.step` (kind "reference": a copy of
+    the reference is found at $MAPF_REFERENCE_ROOT, /root/reference or baseline/_ref; the uninstalled gym / colorama
+    imports are stubbed by oracle/ref_shim.py) -- else through the pure-Python port (kind "port").  A step = one bounded
+    window of sequential env-steps in every process, sized so that the whole run stays within about two minutes."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -175,11 +332,12 @@ def run_reference(args):
     n = max(1, args.steps + args.warmup)
     per_step = max(0.05, min(6.0, 100.0 / n))
     cores = os.cpu_count() or 1
+    kind = reference_kind()
     vals, sample = [], ""
     with mp.get_context("spawn").Pool(cores) as pool:
-        pool.map(_py_worker, [(0.05, i) for i in range(cores)])  # start the workers before anything is timed
+        pool.map(_py_worker, [(0.05, i, kind) for i in range(cores)])  # start the workers before anything is timed
         for i in range(args.warmup + args.steps):
-            v, cores, sample = cpu_python_port(per_step, pool)
+            v, sample = cpu_python(per_step, pool, kind, cores)
             if i >= args.warmup:
                 vals.append(v)
     value = sum(vals) / len(vals)
@@ -188,10 +346,8 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int64+f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": "port",
-                             "sample": sample + " per step (the reference is pure Python and cannot be compiled into "
-                                                "oracle/_ref; this is oracle/mapf_oracle.py)",
-                             "c_port_value": c_val, "c_port_sample": c_sample},
+            "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": cores, "kind": kind,
+                             "sample": sample + " per step", "c_port_value": c_val, "c_port_sample": c_sample},
             "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.time() - t_all}
     print(json.dumps(line), flush=True)
@@ -222,12 +378,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL writes its version / debug lines to stdout when NCCL_DEBUG is set: keep stdout for the one JSON line by
-        # pointing file descriptor 1 at stderr while the communicator comes up (first collective included)
+        # pointing file descriptor 1 at stderr while the communicator comes up (first collective included).  A short
+        # timeout turns any mismatch of collectives into an error within two minutes instead of a spinning GPU.
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -236,7 +393,7 @@ def run_ours(args):
             os.close(saved)
     env = make_env(device=local)
     eng = env.engine
-    B, K, W = ENVS_PER_GPU, args.steps, args.warmup
+    B, K, W = ENVS_PER_GPU, args.steps, max(args.warmup, 3)
     from gym_mapf_b200 import sharding
     shard = sharding.env_shard(world * B, world, rank)   # contiguous slice of the global env batch, no exchange step
     assert shard.count == B
@@ -269,7 +426,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(W, 3)):
+    def max_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(W):
         one_step(i)
     barrier()
 
@@ -287,39 +450,45 @@ def run_ours(args):
         with torch.cuda.graph(graph):
             for i in range(K):
                 one_step(i)
-        barrier()
 
-    # ---- timed region: exactly K steps per repetition, CUDA events on the launching stream; repetitions until the
-    # GPU has been busy long enough for nvidia-smi to sample clocks under load.  The median repetition is reported.
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.15)
-    reps_ms = []
-    t_wall0 = time.time()
-    while True:
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    def k_steps():
         if graph is not None:
             graph.replay()
         else:
             for i in range(K):
                 one_step(i)
-        e1.record()
-        barrier()
-        reps_ms.append(e0.elapsed_time(e1))
-        if args.reps > 0 and len(reps_ms) >= args.reps:
-            break
-        if args.reps == 0 and len(reps_ms) >= 3 and time.time() - t_wall0 > args.min_seconds:
-            break
+
+    # ---- number of repetitions: decided ONCE and COLLECTIVELY (every rank derives it from the same all-reduced
+    # calibration time), so that all ranks issue exactly the same sequence of collectives.  A rank-local wall-clock exit
+    # from the loop let ranks disagree by one repetition and hang in mismatched NCCL calls (round 1, N = 8).
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    k_steps()
+    e1.record()
+    torch.cuda.synchronize()
+    cal_ms = max_ranks(e0.elapsed_time(e1))
+    reps = args.reps if args.reps > 0 else int(min(MAX_REPS, max(3, math.ceil(args.min_seconds * 1e3 / max(cal_ms, 1e-3)))))
+
+    # ---- timed region: `reps` repetitions of exactly K steps, each bracketed by its own pair of CUDA events on the
+    # launching stream; one barrier + synchronize before the first and after the last (none in between: the GPU runs
+    # the repetitions back to back, long enough for nvidia-smi to sample clocks under load).  The median repetition
+    # is reported, max over ranks.
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    barrier()
+    t_wall0 = time.time()
+    for a, b in ev:
+        a.record()
+        k_steps()
+        b.record()
+    barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1)
-    reps_sorted = sorted(reps_ms)
-    ms_total = reps_sorted[len(reps_sorted) // 2]
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    reps_sorted = sorted(a.elapsed_time(b) for a, b in ev)
+    ms_total = max_ranks(reps_sorted[len(reps_sorted) // 2])
     ms_per_step = ms_total / K
     value = world * B * K / (ms_total * 1e-3)
 
@@ -329,6 +498,16 @@ def run_ours(args):
     flags = done.to(torch.uint8) + 2 * coll.to(torch.uint8)
     cs = eng.checksum(ns, prob, reward, flags, index_base=env_offset)
     shard_sums = [[int(x) for x in words] for words in sharding.gather_words(cs)]
+    # sample of the timed variant's last launch (Philox, two envs per thread, auto-reset) for the oracle check below
+    m = 1 << 18
+    head_payload = None
+    if rank == 0 and not args.no_cpu:
+        head_payload = {"kind": "step", "spec": None, "s_lo": states[j][:m].cpu().numpy().view(np.uint64).copy(),
+                        "s_hi": np.zeros(m, np.uint64), "action": actions[j][:m].cpu().numpy().astype(np.int64),
+                        "seed": seed, "step_index": 1000 + K - 1, "env_offset": env_offset, "auto_reset": True,
+                        "s0": int(eng.s0), "next_lo": ns[:m].cpu().numpy().view(np.uint64).copy(), "next_hi": np.zeros(m, np.uint64),
+                        "reward": reward[:m].cpu().numpy(), "prob": prob[:m].cpu().numpy(),
+                        "done": done[:m].cpu().numpy().astype(np.uint8), "collision": coll[:m].cpu().numpy().astype(np.uint8)}
 
     # ---- end to end through the host-buffer C-ABI call: pinned host inputs -> H2D -> step -> D2H, every step
     e2e = None
@@ -350,24 +529,36 @@ def run_ours(args):
         for i in range(n_e2e):
             eng.step_host(hs, ha, hout, seed=seed, step_index=10 + i, env_offset=env_offset, auto_reset=True)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * n_e2e / float(dt.item()), "unit": "transitions/s",
+        dt = max_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * B * n_e2e / dt, "unit": "transitions/s",
                "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": B * 26 * world, "steps": n_e2e,
                "api": "mapf_step_host (C ABI, pinned host buffers in and out)",
-               "host_numa_bind": prev_affinity is not None}
+               "host_numa_bind": prev_affinity is not None,
+               "host_link_gbs": world * B * 38 * n_e2e / dt / 1e9}
+        ceil_path = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
+        if os.path.exists(ceil_path):  # measured PCIe ceilings of this pool's boxes (tools/pcie_peak.py), if committed
+            with open(ceil_path) as f:
+                ceil = json.load(f).get(str(world))
+            if ceil:
+                e2e["pcie_ceiling_gbs"] = ceil
+                e2e["pcie_frac"] = e2e["host_link_gbs"] / ceil["both_total_gbs"]
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)
+
+    # ---- every other BASELINE.json config (device-timed, then checked against the oracle on rank 0)
+    others = []
+    if not args.no_other:
+        from tools import bench_configs
+        others = bench_configs.run_all(local, world, rank, only=set(args.only.split(",")) if args.only else None,
+                                       quick=args.quick)
 
     if rank == 0:
         peak, peak_src = load_peaks()
         achieved = B * STEP_BYTES / (ms_per_step * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": max(W, 3),
+        line = {"metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int64+f64", "data": "synthetic", "config": workload_config(world),
-                "reps": len(reps_ms), "rep_ms_min_med_max": [reps_sorted[0], reps_sorted[len(reps_sorted) // 2],
-                                                             reps_sorted[-1]],
+                "reps": reps, "rep_ms_min_med_max": [reps_sorted[0], reps_sorted[len(reps_sorted) // 2], reps_sorted[-1]],
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_ENV * B,
                              "traffic_source": "ncu --set full, profiles/r01_h_step_8m_raw.csv: dram__bytes_read 100.7 MB "
@@ -382,13 +573,37 @@ def run_ours(args):
                            else "K stream launches"),
                 "shard_checksums": {"keys": ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi",
                                              "sum_prob_bits", "sum_reward_bits", "ordered"], "per_gpu": shard_sums}}
+        if not args.no_cpu:
+            head_payload["spec"] = {"rows": ["".join("@" if v else "." for v in r) for r in env.grid.obstacles],
+                                    "n_agents": env.n_agents, "goals": env.agents_goals, "fail_prob": FAIL_PROB,
+                                    "r_clash": R_CLASH, "r_goal": R_GOAL, "r_living": R_LIVING, "soc": True}
+            ok, what = verify_payload(head_payload)
+            line["parity"] = ok
+            line["parity_sample"] = "last timed launch of the bench kernel: " + what
+            block = {}
+            for name, entry, payload in others:
+                ok, what = verify_payload(payload)
+                entry["parity"] = ok
+                entry["parity_sample"] = what
+                block[name] = entry
+            if block:
+                line["other_configs"] = block
+                line["other_configs_all_parity"] = all(e["parity"] for e in block.values())
+        elif others:
+            line["other_configs"] = {name: entry for name, entry, _ in others}
         if world == 1 and not args.no_cpu:
+            import multiprocessing as mp
             c_val, c_cores, c_sample = cpu_c_port(env, 4.0)
-            p_val, p_cores, p_sample = cpu_python_port(3.0)
+            kind = reference_kind()
+            with mp.get_context("spawn").Pool(c_cores) as pool:
+                pool.map(_py_worker, [(0.05, i, kind) for i in range(c_cores)])
+                p_val, p_sample = cpu_python(3.0, pool, kind, c_cores)
             line["cpu_baseline"] = {"value": c_val, "unit": "transitions/s", "cores": c_cores, "kind": "port",
-                                    "sample": c_sample, "python_port_value": p_val, "python_port_sample": p_sample}
+                                    "sample": c_sample, "python_value": p_val, "python_kind": kind,
+                                    "python_sample": p_sample}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -400,9 +615,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reps", type=int, default=0, help="timed repetitions of the K-step region (0 = auto, >= ~1.5 s)")
     ap.add_argument("--min-seconds", type=float, default=1.5)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the oracle checks")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of a CUDA graph")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block")
+    ap.add_argument("--only", default="", help="comma-separated other_configs cases to run")
+    ap.add_argument("--quick", action="store_true", help="smaller other_configs cases (smoke runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

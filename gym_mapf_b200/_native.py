@@ -233,6 +233,18 @@ class Engine:
                                      or not uniforms.is_contiguous() or uniforms.device != self.torch_device):
             raise ValueError("uniforms must be a contiguous float64 tensor of shape (%d, %d) on %s" % (B, self.n, self.torch_device))
 
+    def _check_tensor(self, name, t, dtype, shape=None, optional=False):
+        """dtype / shape / device / contiguity of one device tensor handed to the library as a raw pointer."""
+        if t is None:
+            if optional:
+                return
+            raise ValueError("%s is required" % name)
+        if t.dtype is not dtype or not t.is_contiguous() or t.device != self.torch_device or \
+                (shape is not None and tuple(t.shape) != tuple(shape)):
+            raise ValueError("%s must be a contiguous %s tensor%s on %s (got %s %s on %s)" % (
+                name, dtype, "" if shape is None else " of shape %s" % (tuple(shape),), self.torch_device, t.dtype,
+                tuple(t.shape), t.device))
+
     def _stream(self):
         import torch
         return torch.cuda.current_stream(self.device_index).cuda_stream
@@ -277,12 +289,15 @@ class Engine:
     def decode(self, states):
         import torch
         B = states.shape[0]
+        self._check_tensor("states", states, torch.int64, self.state_shape(B))
         cells = torch.empty((B, self.n), dtype=torch.int32, device=self.torch_device)
         check(lib().mapf_decode_states(self._h, _ptr(states), B, _ptr(cells), self._stream()))
         return cells
 
     def encode(self, cells):
+        import torch
         B = cells.shape[0]
+        self._check_tensor("cells", cells, torch.int32, (B, self.n))
         states = self.new_states(B)
         check(lib().mapf_encode_states(self._h, _ptr(cells), B, _ptr(states), self._stream()))
         return states
@@ -373,6 +388,10 @@ class Engine:
         import torch
         B = states.shape[0]
         dev = self.torch_device
+        T = int(T)
+        self._check_tensor("states", states, torch.int64, self.state_shape(B))
+        self._check_tensor("actions", actions, torch.int32, (T, B), optional=True)
+        self._check_tensor("uniforms", uniforms, torch.float64, (T, B, self.n), optional=True)
         if out is None:
             out = (torch.empty((T,) + self.state_shape(B), dtype=torch.int64, device=dev),
                    torch.empty((T, B), dtype=torch.float64, device=dev),
@@ -398,7 +417,10 @@ class Engine:
         """Q[b] = sum over P[states[b]][actions[b]], in order, of p * (r + gamma * V[s2]) -- no table is written."""
         import torch
         B = states.shape[0]
+        self._check_batch(states, actions)
+        self._check_tensor("V", V, torch.float64, (V.shape[0],))
         Q = out if out is not None else torch.empty(B, dtype=torch.float64, device=self.torch_device)
+        self._check_tensor("Q", Q, torch.float64, (B,))
         check(lib().mapf_backup(self._h, _ptr(states), _ptr(actions), B, _ptr(V), V.shape[0], float(gamma), _ptr(Q),
                                 self._stream()))
         return Q
@@ -407,7 +429,9 @@ class Engine:
         """The same for the slab [s_begin, s_begin + n_states) x all actions: Q[n_states, nA]."""
         import torch
         sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
+        self._check_tensor("V", V, torch.float64, (V.shape[0],))
         Q = out if out is not None else torch.empty((n_states, self.nA), dtype=torch.float64, device=self.torch_device)
+        self._check_tensor("Q", Q, torch.float64, (n_states, self.nA))
         check(lib().mapf_backup_range(self._h, C.byref(sb), n_states, _ptr(V), V.shape[0], float(gamma), _ptr(Q),
                                       self._stream()))
         return Q
@@ -437,6 +461,7 @@ class Engine:
         """CSR (row_ptr, pred_states) of MapfEnv.predecessors for every state."""
         import torch
         B = states.shape[0]
+        self._check_tensor("states", states, torch.int64, self.state_shape(B))
         row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
         check(lib().mapf_count_predecessors(self._h, _ptr(states), B, _ptr(row_len), self._stream()))
         row_ptr = self._scan(row_len)
@@ -448,6 +473,7 @@ class Engine:
         """The states as the sub-env of `agents` (get_local_view) numbers them: int64[B] or int64[B, 2]."""
         import torch
         B = states.shape[0]
+        self._check_tensor("states", states, torch.int64, self.state_shape(B))
         agents = np.ascontiguousarray(agents, dtype=np.int32)
         words = lib().mapf_projected_words(self._h, len(agents))
         if words < 0:

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -163,6 +164,20 @@ extern "C" void mapf_ctx_destroy(mapf_ctx *ctx) {
             if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
     }
     delete ctx;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a cap PER FUNCTION, and the kernel functions are shared by every
+// context with the same (agents, words, staged): keep a running maximum per (device, function) and never lower it -- a
+// later, smaller context would otherwise shrink the cap under an earlier, larger one and its launches would fail.
+static int raise_smem_cap(int device, const void *fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> cap;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = cap[std::make_pair(device, fn)];
+    if (bytes <= cur || bytes <= 48 * 1024) return MAPF_OK;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+    return MAPF_OK;
 }
 
 static int occupancy_grid(const void *fn, int threads, size_t smem, int sm_count, int *grid) {
@@ -407,8 +422,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
             mapf_ctx_destroy(ctx);
             return fail(MAPF_ERR_UNSUPPORTED, "the %dx%d obstacle bitmap (%zu B) does not fit shared memory", H, W, bm_smem);
         }
-        if (bm_smem > 48 * 1024)
-            CTX_TRY(cudaFuncSetAttribute(k_build_moves, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bm_smem));
+        if (int rc = raise_smem_cap(device, (const void *)k_build_moves, bm_smem)) { mapf_ctx_destroy(ctx); return rc; }
         PatternList pats;
         memset(&pats, 0, sizeof(pats));
         pats.count = ctx->n_patterns;
@@ -437,10 +451,12 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         return fail(MAPF_ERR_UNSUPPORTED, "no kernels for %d agents with %d-word states", n, sp.words);
     }
     ctx->threads = 512;  // two CTAs per SM stage the shared-memory image half as often as four of 256 (measured faster)
-    if (const char *e = getenv("MAPF_THREADS")) {  // tuning experiments only
+#ifdef MAPF_TUNING  // experiment builds only (make variant EXTRA=-DMAPF_TUNING): the release library reads no environment
+    if (const char *e = getenv("MAPF_THREADS")) {
         const int t = atoi(e);
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
     }
+#endif
     // (the shared-memory kernels also estimate chunk quotients in fp64, which needs L**4 < 2**52 and L*L < 2**31)
     const bool luts = sp.divL.fix == 0 && (u128)sp.LL * sp.LL < ((u128)1 << 52) && sp.LL < (1u << 31) &&
                       MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.backup_slab_bytes <= smem_limit;
@@ -513,14 +529,19 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.backup_range, ctx->smem_backup, &ctx->grid_backup_range}};
     for (auto &pl : plan) {
         if (!pl.fn) continue;  // two-word states have no backup kernels; the lane-per-agent step covers 2..8 agents
-        if (pl.smem > 48 * 1024)
-            CTX_TRY(cudaFuncSetAttribute(pl.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-        int rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
+        if (pl.smem > smem_limit) {
+            mapf_ctx_destroy(ctx);
+            return fail(MAPF_ERR_UNSUPPORTED, "a hot kernel needs %zu B of shared memory, the device offers %zu", pl.smem, smem_limit);
+        }
+        int rc = raise_smem_cap(device, pl.fn, pl.smem);
+        if (!rc) rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
         if (rc) { mapf_ctx_destroy(ctx); return rc; }
-        if (const char *e = getenv("MAPF_BLOCKS_PER_SM")) {  // tuning experiments only
+#ifdef MAPF_TUNING
+        if (const char *e = getenv("MAPF_BLOCKS_PER_SM")) {
             const int bps = atoi(e);
             if (bps >= 1 && bps * sm_count <= *pl.grid) *pl.grid = bps * sm_count;
         }
+#endif
     }
     ctx->grid_plain = sm_count * 8;
 
@@ -899,11 +920,15 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
     if (!uniforms && !ctx->philox_ok)
         return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
     const size_t sw = (size_t)ctx->sp.words * 8;
+#ifdef MAPF_TUNING
     static int force_ept = -1;
     if (force_ept < 0) {
         const char *e = getenv("MAPF_STEP_EPT");
         force_ept = e ? atoi(e) : 0;
     }
+#else
+    constexpr int force_ept = 0;
+#endif
     for (int64_t off = 0; off < B; off += MAPF_LAUNCH_MAX_ENVS) {
         const int64_t nb64 = B - off < MAPF_LAUNCH_MAX_ENVS ? B - off : MAPF_LAUNCH_MAX_ENVS;
         DevSpec sp = ctx->sp;
@@ -932,11 +957,15 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             grid = grid_for(nb, ctx->threads, ctx->grid_step1);
         }
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+#ifdef MAPF_TUNING
         static int use_pdl = -1;
         if (use_pdl < 0) {
             const char *e = getenv("MAPF_PDL");
             use_pdl = e ? atoi(e) : 1;
         }
+#else
+        constexpr int use_pdl = 1;
+#endif
         if (use_pdl) {
             // programmatic stream serialization: this launch may begin (up to its griddepcontrol.wait) while the
             // previous kernel of the stream is still draining
@@ -1079,7 +1108,11 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         const void *host_in[3] = {states, actions, uniforms};
         void *host_out[5] = {next_states, reward, prob, done, collision};
         void *dev_in[3] = {nullptr, nullptr, nullptr}, *dev_out[5];
+#ifdef MAPF_TUNING
         bool mapped = getenv("MAPF_HOST_STAGED") == nullptr;
+#else
+        bool mapped = true;
+#endif
         for (int i = 0; i < 3 && mapped; ++i) {
             if (!host_in[i]) continue;
             cudaPointerAttributes at;
@@ -1399,14 +1432,14 @@ extern "C" int mapf_group_create(mapf_ctx *const *ctxs, const int64_t *env_count
     GRP_TRY(cudaMalloc(&g->d_seg, sizeof(u32) * seg.size()));
     GRP_TRY(cudaMemcpy(g->d_seg, seg.data(), sizeof(u32) * seg.size(), cudaMemcpyHostToDevice));
     int grid_p = 0, grid_t = 0;
-    for (const void *fn : {g->fn_philox, g->fn_tape})
-        if (g->smem > 48 * 1024) GRP_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem));
     cudaDeviceProp prop;
     GRP_TRY(cudaGetDeviceProperties(&prop, g->device));
     if (g->smem > (size_t)prop.sharedMemPerBlockOptin) {
         mapf_group_destroy(g);
         return fail(MAPF_ERR_UNSUPPORTED, "the group's largest image needs %zu B of shared memory", g->smem);
     }
+    for (const void *fn : {g->fn_philox, g->fn_tape})
+        if (int rc = raise_smem_cap(g->device, fn, g->smem)) { mapf_group_destroy(g); return rc; }
     int rc = occupancy_grid(g->fn_philox, g->threads, g->smem, c0->info.sm_count, &grid_p);
     if (!rc) rc = occupancy_grid(g->fn_tape, g->threads, g->smem, c0->info.sm_count, &grid_t);
     if (rc) { mapf_group_destroy(g); return rc; }

@@ -1,0 +1,161 @@
+"""GPU tests added in round 2: contexts that share kernel functions, the host/device state mirror of VecMapfEnv,
+host-side validation of every batched entry point, and the bench's own oracle checker on small cases."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch as t
+    return t
+
+
+def _env(name, scen, n, soc=True):
+    from gym_mapf_b200.envs.mapf_env import OptimizationCriteria
+    from gym_mapf_b200.envs.utils import create_mapf_env
+    crit = OptimizationCriteria.SoC if soc else OptimizationCriteria.Makespan
+    return create_mapf_env(name, scen, n, 0.2, -1000.0, 100.0, -1.0, crit, device=0)
+
+
+def _oracle(env, soc=True):
+    from oracle import c_oracle
+    rows = ["".join("@" if v else "." for v in r) for r in env.grid.obstacles]
+    return c_oracle.COracle(rows, env.n_agents, env.agents_goals, 0.2, -1000.0, 100.0, -1.0, soc)
+
+
+def _check_step(torch, env, B=20000, seed=3):
+    eng, ora = env.engine, _oracle(env)
+    rng = np.random.default_rng(seed)
+    cells = rng.integers(0, eng.L, (B, eng.n)).astype(np.int32)
+    lo, hi = ora.encode(cells)
+    actions = rng.integers(0, eng.nA, B).astype(np.int32)
+    uniforms = rng.random((B, eng.n))
+    want = ora.step(lo, hi, actions.astype(np.int64), uniforms)
+    st = eng.encode(torch.from_numpy(cells).cuda())
+    ns, reward, prob, done, coll = eng.step(st, torch.from_numpy(actions).cuda(), uniforms=torch.from_numpy(uniforms).cuda())
+    arr = ns.cpu().numpy().view(np.uint64)
+    glo = arr if eng.words == 1 else arr.reshape(-1, 2)[:, 0]
+    assert np.array_equal(glo, want["next_lo"])
+    assert np.array_equal(reward.cpu().numpy().view(np.uint64), want["reward"].view(np.uint64))
+    assert np.array_equal(prob.cpu().numpy().view(np.uint64), want["prob"].view(np.uint64))
+    tr = eng.transitions(st[:500], torch.from_numpy(actions[:500]).cuda())
+    w = ora.rows(lo[:500], hi[:500], actions[:500].astype(np.int64))
+    assert np.array_equal(tr[0].cpu().numpy(), w["row_ptr"])
+    assert np.array_equal(tr[2].cpu().numpy().view(np.uint64), w["prob"].view(np.uint64))
+
+
+def test_contexts_sharing_kernels_in_decreasing_table_size(torch):
+    """Two contexts with the same agent count share the kernel functions; the second one's smaller staged table must not
+    lower the dynamic shared-memory cap under the first (cudaFuncSetAttribute is per function)."""
+    big = _env("room-64-64-16", 1, 4)     # 3648 cells: 146 KB move table
+    _check_step(torch, big)
+    small = _env("room-64-64-8", 1, 4)    # 3232 cells: 129 KB
+    _check_step(torch, small)
+    smaller = _env("room-32-32-4", 1, 4)  # 27 KB
+    _check_step(torch, smaller)
+    _check_step(torch, big, seed=4)       # launches of the FIRST context still fit
+    _check_step(torch, small, seed=5)
+    from gym_mapf_b200 import _native
+    grp_big = _native.Group([big.engine, small.engine], [3000, 3000])
+    grp_small = _native.Group([smaller.engine], [1000])
+    st = torch.cat([big.engine.states_from_ints([big.engine.s0] * 3000), small.engine.states_from_ints([small.engine.s0] * 3000)])
+    ac = torch.zeros(6000, dtype=torch.int32, device="cuda")
+    grp_small.step(smaller.engine.states_from_ints([smaller.engine.s0] * 1000), ac[:1000])
+    out = grp_big.step(st, ac, seed=1)  # the larger group, after a smaller one was created
+    torch.cuda.synchronize()
+    assert out[0].shape[0] == 6000
+
+
+def test_vec_env_host_and_device_steps_interleave(torch):
+    """step_host continues from wherever the last step / reset / set_states / rollout left the states, and the device
+    path continues from the host mirror (the mirror went stale)."""
+    from gym_mapf_b200.envs.vec_env import VecMapfEnv
+    env = _env("room-32-32-4", 1, 4)
+    B = 3000
+    for reuse in (False, True):
+        a = VecMapfEnv(env, B, seed=11, reuse_outputs=reuse)   # mixed host / device steps
+        b = VecMapfEnv(env, B, seed=11)                         # device only
+        rng = np.random.default_rng(1)
+        plan = ["dev", "host", "host", "dev", "rollout", "host", "reset", "host", "dev", "set", "host", "dev"]
+        for what in plan:
+            acts = rng.integers(0, env.nA, B).astype(np.int32)
+            if what == "reset":
+                a.reset(); b.reset()
+                continue
+            if what == "set":
+                st = b.states.clone()
+                st[: B // 2] = b.states_from_ints([env.s] * (B // 2))
+                a.set_states(st); b.set_states(st)
+                continue
+            if what == "rollout":
+                ra = a.rollout(3); rb = b.rollout(3)
+                assert torch.equal(ra.next_state, rb.next_state)
+                continue
+            want = b.step(torch.from_numpy(acts).cuda())
+            if what == "dev":
+                got = a.step(torch.from_numpy(acts).cuda())
+                assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+            else:
+                got = a.step_host(torch.from_numpy(acts).pin_memory())
+                assert np.array_equal(got[0].numpy(), want[0].cpu().numpy()), what
+                assert np.array_equal(got[1].numpy().view(np.uint64), want[1].cpu().numpy().view(np.uint64))
+                assert np.array_equal(got[3].numpy(), want[2].cpu().numpy())
+
+
+def test_validation_of_every_batched_entry_point(torch):
+    env = _env("room-32-32-4", 1, 4)
+    eng = env.engine
+    st = eng.states_from_ints([eng.s0] * 8)
+    with pytest.raises(ValueError):
+        eng.rollout(st.to(torch.int32), None, 4)
+    with pytest.raises(ValueError):
+        eng.rollout(st, torch.zeros((8, 4), dtype=torch.int32, device="cuda"), 4)   # [B, T] instead of [T, B]
+    with pytest.raises(ValueError):
+        eng.rollout(st, torch.zeros((4, 8), dtype=torch.int64, device="cuda"), 4)
+    with pytest.raises(ValueError):
+        eng.rollout(st, None, 4, uniforms=torch.zeros((4, 8, 3), dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.decode(st.cpu())
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros((8, 3), dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        eng.predecessors(st.to(torch.float64))
+    with pytest.raises(ValueError):
+        eng.project(st[::2], [0, 1])
+    small = _env("empty-8-8", 1, 2, soc=False)
+    e2 = small.engine
+    V = torch.zeros(e2.nS, dtype=torch.float64, device="cuda")
+    s2 = e2.states_from_ints([e2.s0] * 4)
+    a2 = torch.zeros(4, dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):
+        e2.backup(s2, a2, V.to(torch.float32), 0.9)
+    with pytest.raises(ValueError):
+        e2.backup(s2, a2.to(torch.int64), V, 0.9)
+    with pytest.raises(ValueError):
+        e2.backup_range(0, 4, V.cpu(), 0.9)
+    assert e2.backup(s2, a2, V, 0.9).shape == (4,)
+
+
+def test_bench_checker_on_small_cases(torch):
+    """bench.py's `other_configs` machinery end to end on reduced sizes: every case must report parity, and the checker
+    must catch a corrupted sample."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from tools import bench_configs
+    cases = bench_configs.run_all(0, 1, 0, only={"c2_step_strong", "c3_table", "c4_step", "c2_expand", "c2_rollout", "c5_n2",
+                                                 "c5_n8", "c5_density_w2"}, quick=True)
+    assert len(cases) == 8
+    for name, entry, payload in cases:
+        ok, what = bench.verify_payload(payload)
+        assert ok, (name, what)
+        assert entry["frac"] > 0 and entry["value"] > 0
+    name, entry, payload = cases[0]
+    payload["reward"] = payload["reward"].copy()
+    payload["reward"][17] += 1.0
+    assert not bench.verify_payload(payload)[0]

@@ -1,0 +1,399 @@
+"""Device-side measurement of every BASELINE.json config other than the bench headline, for bench.py's `other_configs`
+block (and `python tools/bench_configs.py` on its own).  Each case returns
+
+    (entry, payload)
+
+`entry` is the JSON-able result (units/s, ms, algorithmic bytes per unit, GB/s, fraction of the measured HBM peak);
+`payload` is a numpy sample of the case's inputs and of what the GPU produced for them, which bench.py compares with
+the CPU oracle OUTSIDE the timed region (nothing here imports oracle/).
+
+Timing: CUDA events on the launching stream after warm-up, median of the repetitions.  Every case writes (and the step
+cases also read) far more than the 126 MB L2 per repetition, so each repetition starts with a cold L2.
+Algorithmic bytes (SURVEY.md 8d, W = bytes of a state): expand W+17 per record + (W+12) per row; table slab W+17 per
+record + 8 per row; step 2W+22 per env-step; rollout W+18 per env-step.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from gym_mapf_b200._native import _ptr, check, lib  # noqa: E402
+from gym_mapf_b200.envs.mapf_env import OptimizationCriteria  # noqa: E402
+from gym_mapf_b200.envs.utils import create_mapf_env  # noqa: E402
+
+FAIL_PROB, R_CLASH, R_GOAL, R_LIVING = 0.2, -1000.0, 100.0, -1.0
+M64 = (1 << 64) - 1
+
+
+def load_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"])
+    return 6650.0
+
+
+def make(map_name, scen, n, soc, device):
+    crit = OptimizationCriteria.SoC if soc else OptimizationCriteria.Makespan
+    return create_mapf_env(map_name, scen, n, FAIL_PROB, R_CLASH, R_GOAL, R_LIVING, crit, device=device)
+
+
+def spec_of(env, soc):
+    return {"rows": ["".join("@" if v else "." for v in r) for r in env.grid.obstacles], "n_agents": env.n_agents,
+            "goals": [list(g) for g in env.agents_goals], "starts": [list(g) for g in env.agents_starts],
+            "fail_prob": FAIL_PROB, "r_clash": R_CLASH, "r_goal": R_GOAL, "r_living": R_LIVING, "soc": bool(soc)}
+
+
+def timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def max_over_ranks(seconds, dev, world):
+    if world <= 1:
+        return seconds
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def split_np(eng, t):
+    arr = t.detach().cpu().numpy().view(np.uint64)
+    if eng.words == 1:
+        return arr.copy(), np.zeros_like(arr)
+    arr = arr.reshape(-1, 2)
+    return arr[:, 0].copy(), arr[:, 1].copy()
+
+
+def random_states(eng, B, rng, dev, window=None, H=None):
+    if window is None:
+        cells = rng.integers(0, eng.L, (B, eng.n))
+    else:  # every agent inside a w x w corner window of an EMPTY map (cell id = col * H + row)
+        cells = rng.integers(0, window, (B, eng.n)) * H + rng.integers(0, window, (B, eng.n))
+    return eng.encode(torch.from_numpy(cells.astype(np.int32)).to(dev))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# expand: count + scan + expand on B random (s, a) rows
+# ----------------------------------------------------------------------------------------------------------------
+def expand_case(tag, env, soc, dev, peak, target_records, seed, window=None, sample_records=1 << 20):
+    eng = env.engine
+    W = eng.words * 8
+    rng = np.random.default_rng(seed)
+    H = len(env.grid.obstacles)
+
+    def draw(B):
+        st = random_states(eng, B, rng, dev, window, H)
+        ac = torch.from_numpy(rng.integers(0, eng.nA, B).astype(np.int32)).to(dev)
+        return st, ac
+    st, ac = draw(4096)
+    rl = torch.empty(4096, dtype=torch.int64, device=dev)
+    check(lib().mapf_count_rows(eng._h, _ptr(st), _ptr(ac), 4096, _ptr(rl), eng._stream()))
+    R = float(rl.double().mean().item())
+    B = max(1024, int(target_records / R))
+    st, ac = draw(B)
+    row_len = torch.empty(B, dtype=torch.int64, device=dev)
+    row_ptr, scratch = eng._scan_buffers(B)
+    s = eng._stream()
+    t_count = timed(lambda: check(lib().mapf_count_scan_rows(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_len), _ptr(row_ptr),
+                                                             _ptr(scratch), s)))
+    total = int(row_ptr[-1].item())
+    ns, prob, reward, flags = eng._alloc_records(total)
+    t_exp = timed(lambda: check(lib().mapf_expand(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_ptr), _ptr(ns), _ptr(prob),
+                                                  _ptr(reward), _ptr(flags), s)))
+    t_all = t_count + t_exp
+    by = total * (W + 17) + B * (W + 12)
+    cs = eng.checksum(ns, prob, reward, flags).cpu().numpy().view(np.uint64)
+    entry = {"workload": tag, "kernel": "k_count_partials + k_scan_final + k_expand", "unit": "records/s",
+             "n_agents": eng.n, "cells": eng.L, "state_bytes": W, "rows": B, "records": total, "mean_row": total / B,
+             "clash_frac": float(cs[1]) / max(total, 1), "moves_in_smem": bool(eng.moves_in_smem),
+             "ms": {"count_scan": t_count * 1e3, "expand": t_exp * 1e3}, "value": total / t_all,
+             "bytes_per_unit": by / total, "gbs": by / t_all / 1e9, "frac": by / t_all / 1e9 / peak,
+             "expand_only_frac": total * (W + 17) / t_exp / 1e9 / peak}
+    # parity sample: the first rows whose records number at most `sample_records`
+    rp = row_ptr.cpu().numpy()
+    nrow = int(np.searchsorted(rp, sample_records, side="right")) - 1
+    nrow = max(1, min(nrow, 8192, B))
+    nrec = int(rp[nrow])
+    s_lo, s_hi = split_np(eng, st[:nrow])
+    n_lo, n_hi = split_np(eng, ns[:nrec])
+    payload = {"kind": "rows", "spec": spec_of(env, soc), "s_lo": s_lo, "s_hi": s_hi,
+               "action": ac[:nrow].cpu().numpy().astype(np.int64), "row_ptr": rp[:nrow + 1].copy(), "next_lo": n_lo,
+               "next_hi": n_hi, "prob": prob[:nrec].cpu().numpy(), "reward": reward[:nrec].cpu().numpy(),
+               "flags": flags[:nrec].cpu().numpy()}
+    del ns, prob, reward, flags
+    return entry, payload
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# table slab of consecutive joint states x all actions (configs[2]); rank g takes its own slab
+# ----------------------------------------------------------------------------------------------------------------
+def table_slab_case(tag, env, soc, dev, peak, n_states, world, rank):
+    eng = env.engine
+    W = eng.words * 8
+    nA = int(eng.nA)
+    s_begin = (eng.s0 + rank * (eng.nS // max(world, 1))) % (eng.nS - n_states)
+    sb = (C.c_uint64 * 2)(s_begin & M64, s_begin >> 64)
+    B = n_states * nA
+    row_len = torch.empty(B, dtype=torch.int64, device=dev)
+    row_ptr, scratch = eng._scan_buffers(B)
+    s = eng._stream()
+    t_count = timed(lambda: check(lib().mapf_count_scan_range(eng._h, C.byref(sb), n_states, _ptr(row_len), _ptr(row_ptr),
+                                                              _ptr(scratch), s)))
+    total = int(row_ptr[-1].item())
+    ns, prob, reward, flags = eng._alloc_records(total)
+    t_exp = timed(lambda: check(lib().mapf_expand_range(eng._h, C.byref(sb), n_states, _ptr(row_ptr), _ptr(ns), _ptr(prob),
+                                                        _ptr(reward), _ptr(flags), s)))
+    t_all = max_over_ranks(t_count + t_exp, dev, world)
+    by = total * (W + 17) + B * 8
+    words = eng.checksum(ns, prob, reward, flags)
+    from gym_mapf_b200 import sharding
+    per_rank = sharding.gather_words(words)
+    tot = torch.tensor([total], dtype=torch.int64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    # parity: checksum words of the slab's first state (all nA rows) against the oracle's table walk
+    first = int(row_ptr[nA].item())
+    w1 = eng.checksum(ns[:first], prob[:first], reward[:first], flags[:first]).cpu().numpy().view(np.uint64)
+    entry = {"workload": tag, "kernel": "k_count_partials<RANGE> + k_scan_final + k_expand<RANGE>", "unit": "records/s",
+             "n_agents": eng.n, "cells": eng.L, "state_bytes": W, "states_per_gpu": n_states, "rows_per_gpu": B,
+             "records_per_gpu": total, "records": int(tot.item()), "mean_row": total / B,
+             "ms": {"count_scan": t_count * 1e3, "expand": t_exp * 1e3}, "value": int(tot.item()) / t_all,
+             "bytes_per_unit": by / total, "gbs": by / (t_count + t_exp) / 1e9,
+             "frac": by / (t_count + t_exp) / 1e9 / peak, "sharding": "one slab per rank at offset rank * (nS // world)",
+             "slab_begin": str(s_begin), "shard_checksums": [[int(x) for x in w] for w in per_rank]}
+    payload = {"kind": "table", "spec": spec_of(env, soc), "s_begin": s_begin, "n_states": 1, "words": [int(x) for x in w1]}
+    del ns, prob, reward, flags
+    return entry, payload
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batched step over a ring of slots (stream launches, or one CUDA graph of K launches for small batches)
+# ----------------------------------------------------------------------------------------------------------------
+def step_case(tag, env, soc, dev, peak, B, world, rank, ring, K, graph, seed=77, sample=1 << 16, env_offset=None):
+    eng = env.engine
+    W = eng.words * 8
+    g = torch.Generator(device=dev)
+    g.manual_seed(4 + rank)
+    env_offset = rank * B if env_offset is None else env_offset
+    states = [eng.states_from_ints([eng.s0]).expand(*eng.state_shape(B)).contiguous()]
+    actions = [torch.randint(0, env.nA, (B,), generator=g, device=dev, dtype=torch.int32) for _ in range(ring)]
+    outs = []
+    for j in range(ring):
+        out = (eng.new_states(B), torch.empty(B, dtype=torch.float64, device=dev),
+               torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.bool, device=dev),
+               torch.empty(B, dtype=torch.bool, device=dev))
+        outs.append(out)
+        eng.step(states[j], actions[j], seed=seed, step_index=j, env_offset=env_offset, auto_reset=True, out=out)
+        if j + 1 < ring:
+            states.append(out[0].clone())
+
+    def run():
+        for i in range(K):
+            j = i % ring
+            eng.step(states[j], actions[j], seed=seed, step_index=100 + i, env_offset=env_offset, auto_reset=True, out=outs[j])
+    fn = run
+    if graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            run()
+        fn = gr.replay
+    t = max_over_ranks(timed(fn, reps=5, warm=1) / K, dev, world)
+    by = B * (2 * W + 22)
+    # parity sample: slot j of the last launch that wrote it
+    i_last = K - 1
+    j = i_last % ring
+    m = min(sample, B)
+    s_lo, s_hi = split_np(eng, states[j][:m])
+    n_lo, n_hi = split_np(eng, outs[j][0][:m])
+    payload = {"kind": "step", "spec": spec_of(env, soc), "s_lo": s_lo, "s_hi": s_hi,
+               "action": actions[j][:m].cpu().numpy().astype(np.int64), "seed": seed, "step_index": 100 + i_last,
+               "env_offset": env_offset, "auto_reset": True, "s0": int(eng.s0), "next_lo": n_lo, "next_hi": n_hi,
+               "reward": outs[j][1][:m].cpu().numpy(), "prob": outs[j][2][:m].cpu().numpy(),
+               "done": outs[j][3][:m].cpu().numpy().astype(np.uint8), "collision": outs[j][4][:m].cpu().numpy().astype(np.uint8)}
+    entry = {"workload": tag, "kernel": "k_step", "unit": "transitions/s", "n_agents": eng.n, "cells": eng.L,
+             "state_bytes": W, "envs_per_gpu": B, "global_envs": B * world, "moves_in_smem": bool(eng.moves_in_smem),
+             "us_per_step": t * 1e6, "value": B * world / t, "bytes_per_unit": 2 * W + 22, "gbs": by / t / 1e9,
+             "frac": by / t / 1e9 / peak, "launch": "one CUDA graph of %d launches" % K if graph else "stream launches",
+             "l2": "ring of %d slots, %.0f MB per cycle" % (ring, ring * by / 1e6)}
+    del states, actions, outs
+    return entry, payload
+
+
+def rollout_case(tag, env, soc, dev, peak, B, T, seed=5, sample=4096):
+    eng = env.engine
+    W = eng.words * 8
+    states0 = eng.states_from_ints([eng.s0]).expand(*eng.state_shape(B)).contiguous()
+    states = states0.clone()
+    out = (torch.empty((T,) + eng.state_shape(B), dtype=torch.int64, device=dev),
+           torch.empty((T, B), dtype=torch.float64, device=dev), torch.empty((T, B), dtype=torch.float64, device=dev),
+           torch.empty((T, B), dtype=torch.bool, device=dev), torch.empty((T, B), dtype=torch.bool, device=dev))
+
+    t = timed(lambda: eng.rollout(states, None, T, seed=seed, step_index=0, auto_reset=True, out=out), reps=5, warm=1) / T
+    states.copy_(states0)  # the sampled call starts from known states
+    eng.rollout(states, None, T, seed=seed, step_index=0, auto_reset=True, out=out)
+    by = B * (W + 18)
+    m = min(sample, B)
+    s_lo, s_hi = split_np(eng, states0[:m])
+    n_lo, n_hi = split_np(eng, out[0][:, :m].contiguous().reshape((T * m,) + ((2,) if eng.words == 2 else ())))
+    payload = {"kind": "rollout", "spec": spec_of(env, soc), "s_lo": s_lo, "s_hi": s_hi, "seed": seed, "step_index": 0,
+               "env_offset": 0, "T": T, "s0": int(eng.s0), "nA": int(eng.nA), "next_lo": n_lo.reshape(T, m),
+               "next_hi": n_hi.reshape(T, m), "reward": out[1][:, :m].cpu().numpy(), "prob": out[2][:, :m].cpu().numpy(),
+               "done": out[3][:, :m].cpu().numpy().astype(np.uint8), "collision": out[4][:, :m].cpu().numpy().astype(np.uint8)}
+    entry = {"workload": tag, "kernel": "k_rollout", "unit": "transitions/s", "n_agents": eng.n, "state_bytes": W,
+             "envs": B, "T": T, "us_per_step": t * 1e6, "value": B / t, "bytes_per_unit": W + 18, "gbs": by / t / 1e9,
+             "frac": by / t / 1e9 / peak, "policy": "random actions drawn on the device (Philox block 15)"}
+    del out
+    return entry, payload
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# configs[0]: the reference's own CPU-runnable case through the drop-in scalar API and through the batched API
+# ----------------------------------------------------------------------------------------------------------------
+def c1_case(dev, peak, device_index):
+    env = make("empty-8-8", 1, 2, False, device_index)
+    eng = env.engine
+    env.P[0][0]  # first launch
+    t0 = time.perf_counter()
+    n = 0
+    for s in range(env.nS):
+        Ps = env.P[s]
+        for a in range(env.nA):
+            n += len(Ps[a])
+    t_table = time.perf_counter() - t0
+    rng = np.random.default_rng(1)
+    acts = rng.integers(0, env.nA, 10000)
+    s = env.reset()
+    trace_s, trace_ns, trace_r, trace_d, trace_p = [], [], [], [], []
+    t0 = time.perf_counter()
+    for a in acts:
+        trace_s.append(s)
+        ns, r, done, info = env.step(int(a))
+        trace_ns.append(ns); trace_r.append(r); trace_d.append(done); trace_p.append(info["prob"])
+        s = env.reset() if done else ns
+    t_steps = time.perf_counter() - t0
+    # the whole table in one batched call
+    sb = (C.c_uint64 * 2)(0, 0)
+    B = env.nS * env.nA
+    row_len = torch.empty(B, dtype=torch.int64, device=dev)
+    row_ptr, scratch = eng._scan_buffers(B)
+    st = eng._stream()
+    check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, _ptr(row_len), _ptr(row_ptr), _ptr(scratch), st))
+    total = int(row_ptr[-1].item())
+    rec = eng._alloc_records(total)
+
+    def table():
+        check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, _ptr(row_len), _ptr(row_ptr), _ptr(scratch), st))
+        check(lib().mapf_expand_range(eng._h, C.byref(sb), env.nS, _ptr(row_ptr), _ptr(rec[0]), _ptr(rec[1]), _ptr(rec[2]),
+                                      _ptr(rec[3]), st))
+    t_b = timed(table, reps=5, warm=2)
+    words = eng.checksum(*rec).cpu().numpy().view(np.uint64)
+    by = total * 25 + B * 8
+    entry = {"workload": "C1: empty-8-8 scen 1, 2 agents, Makespan: full P table (4096 x 25 rows) + 10k random-policy steps",
+             "unit": "transitions/s", "records": total,
+             "scalar_api": {"table_s": t_table, "transitions": n, "transitions_per_s": n / t_table, "steps_s": t_steps,
+                            "steps_per_s": len(acts) / t_steps,
+                            "note": "the reference's own loop `for s: for a: env.P[s][a]` and 10 000 env.step() calls, "
+                                    "each served by a GPU launch (64 states of P per k_expand call)"},
+             "batched_api": {"table_ms": t_b * 1e3, "value": total / t_b, "gbs": by / t_b / 1e9, "frac": by / t_b / 1e9 / peak,
+                             "note": "16.7 MB of records: launch-latency bound, three launches"},
+             "value": total / t_b, "bytes_per_unit": by / total, "frac": by / t_b / 1e9 / peak}
+    payload = {"kind": "c1", "spec": spec_of(env, False), "nS": int(env.nS), "words": [int(x) for x in words],
+               "scalar_transitions": n, "acts": acts.astype(np.int64), "trace_s": trace_s, "trace_ns": trace_ns,
+               "trace_r": trace_r, "trace_d": trace_d, "trace_p": trace_p}
+    return entry, payload
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def run_all(device_index, world, rank, only=None, quick=False):
+    """-> list of (name, entry, payload).  Cases that shard (C3 slab, C4 step, C2 strong scaling) run on every rank and
+    reduce their time over the ranks; the single-GPU cases run when world == 1."""
+    dev = torch.device("cuda", device_index)
+    peak = load_peak()
+    out = []
+    target = (1 << 24) if quick else (1 << 26)
+
+    def want(name):
+        return only is None or name in only
+
+    def add(name, fn):
+        if want(name):
+            t0 = time.perf_counter()
+            entry, payload = fn()
+            entry["wall_s"] = time.perf_counter() - t0
+            out.append((name, entry, payload))
+            torch.cuda.empty_cache()
+
+    # ---- sharded cases (every rank)
+    add("c2_step_strong", lambda: step_case(
+        "C2 strong scaling: room-32-32-4 scen 1, 4 agents, SoC; 2**20 GLOBAL envs split over %d GPU(s)" % world,
+        make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, (1 << 20) // world, world, rank, ring=32 * world,
+        K=64, graph=True))
+    add("c3_table", lambda: table_slab_case(
+        "C3: maze-32-32-4 scen 10, 6 agents, Makespan; slab of consecutive joint states x 15625 actions per GPU",
+        make("maze-32-32-4", 10, 6, False, device_index), False, dev, peak, 4 if quick else 16, world, rank))
+    add("c4_step", lambda: step_case(
+        "C4: room-64-64-8 scen 1, 8 agents, Makespan, 128-bit states; 2**24 GLOBAL envs split over %d GPU(s)" % world,
+        make("room-64-64-8", 1, 8, False, device_index), False, dev, peak, ((1 << 20) if quick else (1 << 24)) // world,
+        world, rank, ring=2 if world == 1 else 2 * world, K=4, graph=False))
+    if world > 1:
+        return out
+    # ---- single-GPU cases
+    add("c1", lambda: c1_case(dev, peak, device_index))
+    add("c2_expand", lambda: expand_case("C2 expand: room-32-32-4 scen 1, 4 agents, SoC; random (s, a) rows",
+                                         make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, target, 2))
+    add("c2_rollout", lambda: rollout_case("C2 rollout: room-32-32-4 scen 1, 4 agents, SoC; 32 steps per launch",
+                                           make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, 1 << 20, 32))
+    for n in range(2, 11):
+        add("c5_n%d" % n, lambda n=n: expand_case("C5 expand: empty-32-32 scen 1, %d agents, SoC; random (s, a) rows" % n,
+                                                  make("empty-32-32", 1, n, True, device_index), True, dev, peak, target,
+                                                  50 + n))
+    for w in (16, 8, 4, 2):
+        add("c5_density_w%d" % w, lambda w=w: expand_case(
+            "C5 conflict density: empty-32-32, 6 agents inside a %dx%d window" % (w, w),
+            make("empty-32-32", 1, 6, True, device_index), True, dev, peak, target, 70 + w, window=w))
+    # ---- maps whose move table does not fit shared memory (3 of the 12 shipped maps)
+    for name, scen, n in (("maze-128-128-10", 2, 4), ("Berlin_1_256", 11, 4)):
+        if want("big_%s_step" % name) or want("big_%s_expand" % name):
+            try:
+                env = make(name, scen, n, True, device_index)
+            except KeyError:
+                continue
+            add("big_%s_step" % name, lambda env=env, name=name: step_case(
+                "large map step: %s scen %d, %d agents, SoC; 2**20 envs" % (name, scen, n), env, True, dev, peak, 1 << 20, 1, 0,
+                ring=32, K=64, graph=True))
+            add("big_%s_expand" % name, lambda env=env, name=name: expand_case(
+                "large map expand: %s scen %d, %d agents, SoC; random (s, a) rows" % (name, scen, n), env, True, dev, peak,
+                target, 90))
+    return out
+
+
+if __name__ == "__main__":
+    only = set(sys.argv[1:]) or None
+    for name, entry, _ in run_all(0, 1, 0, only=only):
+        print(json.dumps({name: entry}), flush=True)
