@@ -7,10 +7,16 @@ batched step over 2**20 parallel envs PER GPU (weak scaling; shards are independ
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # our arm
     python bench.py --impl reference [--steps K] [--warmup W]           # the reference's own CPU path on the host cores
 
-A "step" = one launch of the step kernel over this rank's 2**20 envs: it reads 8 B state + 4 B action and writes
+A "step" = one pass of the step kernel over this rank's 2**20 envs: it reads 8 B state + 4 B action and writes
 8 B next state + 8 B reward + 8 B probability + 1 B done + 1 B collision per env (38 B), drawing the
 slip uniforms on the device (Philox4x32-10).  Steps cycle over a ring of pre-filled (state, action, output) slots
 whose total footprint (>= 8x the 126 MB L2) keeps every timed launch reading from and writing to HBM.
+
+The rank's envs are held as `--pools` (default 2) independent pools of 2**20 / pools envs, each stepped on its own CUDA
+stream with one resident CTA per SM (MAPF_OPT_SHARE_SM): every pool is a chain of launches, each ordered after the
+previous launch of ITS pool (programmatic dependent launch), and the two chains share every SM -- while one pool's
+launch drains and the next one waits for it, the other pool computes.  One step = `pools` launches; `gpu_launches`
+counts them all.  `--pools 1` is the single chain of full-GPU launches (also reported, as `single_chain`).
 
 Besides the headline the line carries `other_configs`: every other BASELINE.json config (C1 full table + 10k steps,
 C2 expand / rollout / strong scaling, C3 table slab per rank, C4 2**24-env 128-bit step, C5 agent-count and
@@ -200,9 +206,12 @@ def verify_payload(p):
         ok = True
         for t in range(T):
             stp = p["step_index"] + t
-            w = philox_block(env_ids, stp, 15, p["seed"])
-            frac = (w[0] << np.uint64(32)) | w[1]
-            act = np.array([(int(f) * p["nA"]) >> 64 for f in frac], dtype=np.int64)  # umul64hi(frac, nA)
+            if p.get("actions") is not None:
+                act = p["actions"][t]
+            else:
+                w = philox_block(env_ids, stp, 15, p["seed"])
+                frac = (w[0] << np.uint64(32)) | w[1]
+                act = np.array([(int(f) * p["nA"]) >> 64 for f in frac], dtype=np.int64)  # umul64hi(frac, nA)
             u = device_uniforms(env_ids, stp, p["seed"], n)
             want = ora.step(lo, hi, act, u, threads=threads)
             nlo = np.where(want["done"] == 1, np.uint64(p["s0"] & M64), want["next_lo"])
@@ -356,7 +365,8 @@ def run_reference(args):
 def workload_config(n_gpus):
     return {"workload": "C2: %s scen %d, %d agents, fail_prob %.1f, SoC; batched step over 2**20 envs per GPU" % (
         MAP, SCEN, N_AGENTS, FAIL_PROB), "envs_per_gpu": ENVS_PER_GPU, "global_envs": ENVS_PER_GPU * n_gpus,
-        "parallelism": "env-sharded x%d, no data-path collective" % n_gpus, "sampling": "device Philox4x32-10",
+        "parallelism": "env-sharded x%d, no data-path collective; per GPU the shard is held as env pools stepped on "
+                       "separate streams (see `pools`)" % n_gpus, "sampling": "device Philox4x32-10",
         "l2": "ring of %d input/output slots (%.1f GB per GPU) cycled so every launch misses the 126 MB L2" % (
             RING_SLOTS, RING_SLOTS * ENVS_PER_GPU * STEP_BYTES / 1e9)}
 
@@ -416,11 +426,6 @@ def run_ours(args):
             states.append(out[0].clone())
     torch.cuda.synchronize()
 
-    def one_step(i):
-        j = i % RING_SLOTS
-        eng.step(states[j], actions[j], seed=seed, step_index=1000 + i, env_offset=env_offset, auto_reset=True,
-                 out=outs[j])
-
     def barrier():
         if world > 1:
             dist.barrier()
@@ -432,63 +437,93 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(W):
-        one_step(i)
-    barrier()
+    def timed_region(pools, reps_fixed, sample_clocks):
+        """K steps per repetition with the envs in `pools` pools; -> (ms per repetition [median, max over ranks], reps,
+        sorted per-repetition ms of this rank, clocks)."""
+        H = B // pools
+        streams = [torch.cuda.Stream() for _ in range(pools)] if pools > 1 else []
 
-    # The K steps of one repetition are captured once into a CUDA graph (K kernel nodes joined by programmatic
-    # dependent-launch edges) and replayed: the host launch path (~13 us per call through Python/ctypes) would
-    # otherwise be as long as the kernel itself.  --no-graph times plain stream launches instead.
-    graph = None
-    if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            one_step(0)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        def one_step(i):
+            j = i % RING_SLOTS
+            if pools == 1:
+                eng.step(states[j], actions[j], seed=seed, step_index=1000 + i, env_offset=env_offset, auto_reset=True,
+                         out=outs[j])
+                return
+            for k, st in enumerate(streams):
+                sl = slice(k * H, (k + 1) * H)
+                with torch.cuda.stream(st):
+                    eng.step(states[j][sl], actions[j][sl], seed=seed, step_index=1000 + i, env_offset=env_offset + k * H,
+                             auto_reset=True, out=tuple(t[sl] for t in outs[j]), share_sm=True)
+
+        def k_steps_eager():
+            cur = torch.cuda.current_stream()
+            for st in streams:
+                st.wait_stream(cur)
             for i in range(K):
                 one_step(i)
+            for st in streams:
+                cur.wait_stream(st)
 
-    def k_steps():
-        if graph is not None:
-            graph.replay()
-        else:
-            for i in range(K):
-                one_step(i)
+        for i in range(W):
+            one_step(i)
+        barrier()
+        # The K steps of one repetition are captured once into a CUDA graph (kernel nodes joined by programmatic
+        # dependent-launch edges, one chain per pool) and replayed: the host launch path (~13 us per call through
+        # Python/ctypes) would otherwise be as long as the kernel itself.  --no-graph times plain stream launches.
+        graph = None
+        if not args.no_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                k_steps_eager()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                k_steps_eager()
+        k_steps = graph.replay if graph is not None else k_steps_eager
 
-    # ---- number of repetitions: decided ONCE and COLLECTIVELY (every rank derives it from the same all-reduced
-    # calibration time), so that all ranks issue exactly the same sequence of collectives.  A rank-local wall-clock exit
-    # from the loop let ranks disagree by one repetition and hang in mismatched NCCL calls (round 1, N = 8).
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    k_steps()
-    e1.record()
-    torch.cuda.synchronize()
-    cal_ms = max_ranks(e0.elapsed_time(e1))
-    reps = args.reps if args.reps > 0 else int(min(MAX_REPS, max(3, math.ceil(args.min_seconds * 1e3 / max(cal_ms, 1e-3)))))
-
-    # ---- timed region: `reps` repetitions of exactly K steps, each bracketed by its own pair of CUDA events on the
-    # launching stream; one barrier + synchronize before the first and after the last (none in between: the GPU runs
-    # the repetitions back to back, long enough for nvidia-smi to sample clocks under load).  The median repetition
-    # is reported, max over ranks.
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.15)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    barrier()
-    t_wall0 = time.time()
-    for a, b in ev:
-        a.record()
+        # ---- number of repetitions: decided ONCE and COLLECTIVELY (every rank derives it from the same all-reduced
+        # calibration time), so that all ranks issue exactly the same sequence of collectives.  A rank-local wall-clock
+        # exit from the loop let ranks disagree by one repetition and hang in mismatched NCCL calls (round 1, N = 8).
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         k_steps()
-        b.record()
-    barrier()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1)
-    reps_sorted = sorted(a.elapsed_time(b) for a, b in ev)
-    ms_total = max_ranks(reps_sorted[len(reps_sorted) // 2])
+        e1.record()
+        torch.cuda.synchronize()
+        cal_ms = max_ranks(e0.elapsed_time(e1))
+        reps = reps_fixed if reps_fixed > 0 else int(min(MAX_REPS, max(3, math.ceil(args.min_seconds * 1e3 / max(cal_ms, 1e-3)))))
+        # ---- timed region: `reps` repetitions of exactly K steps, each bracketed by its own pair of CUDA events on
+        # the launching stream; one barrier + synchronize before the first and after the last (none in between: the
+        # GPU runs the repetitions back to back, long enough for nvidia-smi to sample clocks under load).  The median
+        # repetition is reported, max over ranks.
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+            time.sleep(0.15)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        barrier()
+        t_wall0 = time.time()
+        for a, b in ev:
+            a.record()
+            k_steps()
+            b.record()
+        barrier()
+        t_wall1 = time.time()
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        reps_sorted = sorted(a.elapsed_time(b) for a, b in ev)
+        return max_ranks(reps_sorted[len(reps_sorted) // 2]), reps, reps_sorted, clocks, graph is not None
+
+    pools = max(1, args.pools)
+    if B % (2 * pools):
+        raise SystemExit("--pools must divide the env batch into even pools")
+    single = None
+    if pools > 1:  # the single chain of full-GPU launches, for comparison (short: a quarter of the timed window)
+        ms1, reps1, _, _, _ = timed_region(1, args.reps, False)
+        single = {"ms_per_step": ms1 / K, "value": world * B * K / (ms1 * 1e-3), "reps": reps1,
+                  "frac": B * STEP_BYTES / (ms1 / K * 1e-3) / 1e9 / load_peaks()[0],
+                  "launch": "one chain of K full-GPU launches (two CTAs per SM), programmatic dependent launch"}
+    ms_total, reps, reps_sorted, clocks, graphed = timed_region(pools, args.reps, True)
     ms_per_step = ms_total / K
     value = world * B * K / (ms_total * 1e-3)
 
@@ -567,10 +602,13 @@ def run_ours(args):
                                                "when the kernel ended, the rest was still in the 126 MB L2)",
                              "peak_source": peak_src,
                              "kernel": "k_step<4,smem move table>", "bytes_per_unit": STEP_BYTES,
-                             "units_per_launch": B},
-                "e2e": e2e, "gpu_launches": K, "clocks": clocks,
-                "launch": ("one CUDA graph of K step kernels (programmatic dependent launch)" if graph is not None
-                           else "K stream launches"),
+                             "units_per_launch": B // pools, "launches_per_step": pools,
+                             "achieved_definition": "38 B x 2**20 envs / (timed region / K steps): the %d launches of a step "
+                                                    "run concurrently, so a step's duration, not a launch's, is what the "
+                                                    "events measure" % pools},
+                "e2e": e2e, "gpu_launches": K * pools, "clocks": clocks, "pools": pools, "single_chain": single,
+                "launch": ("one CUDA graph of K x %d step kernels: %d env pool(s), one stream and one chain of programmatic "
+                           "dependent launches per pool" % (pools, pools) if graphed else "K x %d stream launches" % pools),
                 "shard_checksums": {"keys": ["count", "n_collision", "n_done", "sum_next_lo", "sum_next_hi",
                                              "sum_prob_bits", "sum_reward_bits", "ordered"], "per_gpu": shard_sums}}
         if not args.no_cpu:
@@ -618,6 +656,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the oracle checks")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of a CUDA graph")
+    ap.add_argument("--pools", type=int, default=2, help="independent env pools per GPU, one stream each (1 = single chain)")
     ap.add_argument("--no-other", action="store_true", help="skip the other_configs block")
     ap.add_argument("--only", default="", help="comma-separated other_configs cases to run")
     ap.add_argument("--quick", action="store_true", help="smaller other_configs cases (smoke runs)")

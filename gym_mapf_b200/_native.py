@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MAPF_B200_LIB", os.path.join(CSRC, "libmapf_b200.so")
 MAPF_OK, MAPF_ERR_INVALID, MAPF_ERR_KEY, MAPF_ERR_UNSUPPORTED, MAPF_ERR_CUDA, MAPF_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
 MAPF_SOC, MAPF_MAKESPAN = 0, 1
 OPT_AUTO_RESET = 1
+OPT_SHARE_SM = 2
 FLAG_DONE, FLAG_COLLISION = 1, 2
 
 EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
@@ -363,9 +364,10 @@ class Engine:
 
     # ---- step / rollout
     def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None,
-             mapping="thread"):
+             mapping="thread", share_sm=False):
         """`mapping`: "thread" (one thread per env, the shipped kernel) or "lanes" (one warp lane per agent, the measured
-        alternative; 2..8 agents, one-word states)."""
+        alternative; 2..8 agents, one-word states).  `share_sm`: one resident CTA per SM (MAPF_OPT_SHARE_SM), for env
+        pools that are stepped concurrently on separate streams."""
         B = states.shape[0]
         self._check_batch(states, actions, uniforms)
         if out is None:
@@ -378,7 +380,8 @@ class Engine:
         fn = self._mapf_step if mapping == "thread" else lib().mapf_step_lanes
         rc = fn(self._h, states.data_ptr(), actions.data_ptr(), B,
                 None if uniforms is None else uniforms.data_ptr(), seed, step_index, env_offset,
-                OPT_AUTO_RESET if auto_reset else 0, ns.data_ptr(), reward.data_ptr(), prob.data_ptr(),
+                (OPT_AUTO_RESET if auto_reset else 0) | (OPT_SHARE_SM if share_sm else 0), ns.data_ptr(),
+                reward.data_ptr(), prob.data_ptr(),
                 done.data_ptr(), coll.data_ptr(), self._stream())
         if rc:
             check(rc)

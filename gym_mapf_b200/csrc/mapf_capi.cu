@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -63,7 +64,7 @@ struct mapf_ctx {
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
     size_t smem_backup = 0;      // smem_base + per-warp backup slabs
-    int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout_tape = 0;
+    int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout2 = 0, grid_rollout_tape = 0;
     int grid_lanes = 0, grid_lanes_tape = 0;
     LaneConsts lanes;                   // per-lane constants of the lane-per-agent step (k_step_lanes)
     int grid_expand = 0, grid_expand_range = 0, grid_plain = 0, grid_backup = 0, grid_backup_range = 0;
@@ -291,7 +292,26 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         const u64 ll = (u64)L * (u64)L;
         sp.LL = (u32)ll;
         sp.divLL = make_fastdiv(ll);
-        sp.invLL = 1.0 / (double)ll;
+        // reciprocals rounded UP (checked exactly in 128-bit integers: inv = m * 2**e with a 53-bit m), see fdiv_floor()
+        auto recip_up = [](u64 d) {
+            double inv = 1.0 / (double)d;
+            for (;;) {
+                int e;
+                const double m = frexp(inv, &e);              // inv = m * 2**e, 0.5 <= m < 1
+                const u64 mi = (u64)ldexp(m, 53);              // 53-bit integer mantissa
+                // inv * d >= 1  <=>  mi * d >= 2**(53 - e)
+                const u128 lhs = (u128)mi * (u128)d;
+                const int sh = 53 - e;
+                if (sh < 127 && lhs >= ((u128)1 << sh)) return inv;
+                inv = nextafter(inv, 2.0);
+            }
+        };
+        sp.invLL_up = recip_up(ll);
+        sp.negcLL = -ldexp(sp.invLL_up, 52);
+        sp.invL_up = recip_up((u64)L);
+        sp.negcL = -ldexp(sp.invL_up, 52);
+        sp.negLL = (u32)(0u - (u32)ll);
+        sp.negL = (u32)(0u - (u32)L);
         // expand with cached head agents (see HeadCache): tail = last six agents
         sp.head_ok = 0;
         sp.powLH = 1;
@@ -457,8 +477,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         if (t >= 32 && t <= MAPF_MAX_THREADS && t % 32 == 0) ctx->threads = t;
     }
 #endif
-    // (the shared-memory kernels also estimate chunk quotients in fp64, which needs L**4 < 2**52 and L*L < 2**31)
-    const bool luts = sp.divL.fix == 0 && (u128)sp.LL * sp.LL < ((u128)1 << 52) && sp.LL < (1u << 31) &&
+    // (the shared-memory kernels also divide chunks on the fp64 pipe, which needs L**4 < 2**50 and L*L < 2**31)
+    const bool luts = sp.divL.fix == 0 && (u128)sp.LL * sp.LL < ((u128)1 << 50) && sp.LL < (1u << 31) &&
                       MAPF_SMEM_LUT + lut_pad + (size_t)(ctx->threads / 32) * probe.backup_slab_bytes <= smem_limit;
     if (!luts) ctx->threads = 256;
     sp.lut_smem = luts ? 1 : 0;
@@ -471,6 +491,10 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         CTX_TRY(cudaMemcpy(&sp.smem_window, d_probe, sizeof(u32), cudaMemcpyDeviceToHost));
         cudaFree(d_probe);
         const u32 act0 = luts ? sp.smem_window + MAPF_SMEM_LUT : 0u;
+        if (sp.smem_window & 0xffu) {  // ent_row() merges a pattern-row offset into the window address with one PRMT
+            mapf_ctx_destroy(ctx);
+            return fail(MAPF_ERR_UNSUPPORTED, "shared-memory window 0x%x is not a multiple of 256", sp.smem_window);
+        }
         if (act0 + 32u > 0xffffu) {
             mapf_ctx_destroy(ctx);
             return fail(MAPF_ERR_UNSUPPORTED, "shared-memory window 0x%x does not fit the 16-bit action table", sp.smem_window);
@@ -515,11 +539,12 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
     ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
     ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
-    struct { const void *fn; size_t smem; int *grid; } plan[] = {
+    struct { const void *fn; size_t smem; int *grid; int threads; } plan[] = {
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
         {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
         {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
+        {ctx->ks.rollout_philox2, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.step_lanes_philox, ctx->smem_base, &ctx->grid_lanes},
         {ctx->ks.step_lanes_tape, ctx->smem_base, &ctx->grid_lanes_tape},
@@ -534,7 +559,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
             return fail(MAPF_ERR_UNSUPPORTED, "a hot kernel needs %zu B of shared memory, the device offers %zu", pl.smem, smem_limit);
         }
         int rc = raise_smem_cap(device, pl.fn, pl.smem);
-        if (!rc) rc = occupancy_grid(pl.fn, ctx->threads, pl.smem, sm_count, pl.grid);
+        if (!rc) rc = occupancy_grid(pl.fn, pl.threads ? pl.threads : ctx->threads, pl.smem, sm_count, pl.grid);
         if (rc) { mapf_ctx_destroy(ctx); return rc; }
 #ifdef MAPF_TUNING
         if (const char *e = getenv("MAPF_BLOCKS_PER_SM")) {
@@ -942,7 +967,16 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         u32 nb = (u32)nb64;
         u64 st = step_index, e0 = (u64)(env_offset + off);
         u32 op = options;
+#ifdef MAPF_TRACE  // timeline builds: the Philox-mode kernel receives the trace buffer in place of the unused uniforms
+        const double *trace_buf = nullptr;
+        if (!uniforms) {
+            if (const char *e = getenv("MAPF_TRACE_PTR")) trace_buf = (const double *)strtoull(e, nullptr, 0);
+        }
+        void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, uniforms ? (void *)&a_u : (void *)&trace_buf, &st, &e0, &op,
+                        &a_ns, &a_r, &a_p, &a_d, &a_c};
+#else
         void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, &a_u, &st, &e0, &op, &a_ns, &a_r, &a_p, &a_d, &a_c};
+#endif
         const void *fn;
         int grid;
         if (uniforms) {
@@ -957,6 +991,7 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             grid = grid_for(nb, ctx->threads, ctx->grid_step1);
         }
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
+        if ((options & MAPF_OPT_SHARE_SM) && grid > ctx->info.sm_count) grid = ctx->info.sm_count;
 #ifdef MAPF_TUNING
         static int use_pdl = -1;
         if (use_pdl < 0) {
@@ -1048,12 +1083,18 @@ extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32
     u32 op = options, nb = (u32)B;
     void *args[] = {&sp, &keys, &states_inout, &actions, &T, &nb, &uniforms, &st, &e0, &op, &next_states, &reward, &prob,
                     &done, &collision};
-    if (uniforms)
+    if (uniforms) {
         LAUNCH(ctx->ks.rollout_tape, grid_for(B, ctx->threads, ctx->grid_rollout_tape), ctx->threads, ctx->smem_base,
                stream, args);
-    else
+    } else if (ctx->ks.rollout_philox2 && (B & 1) == 0 && aligned(states_inout, 16) && aligned(next_states, 16) && (!actions || aligned(actions, 8)) &&
+               aligned(reward, 16) && aligned(prob, 16) && aligned(done, 2) && aligned(collision, 2)) {
+        // two envs per thread, 128-bit stores: every slab t * B of the [T, B] outputs keeps the base alignment (B even)
+        LAUNCH(ctx->ks.rollout_philox2, grid_for(B / 2, MAPF_ROLLOUT2_THREADS, ctx->grid_rollout2), MAPF_ROLLOUT2_THREADS,
+               ctx->smem_base, stream, args);
+    } else {
         LAUNCH(ctx->ks.rollout_philox, grid_for(B, ctx->threads, ctx->grid_rollout), ctx->threads, ctx->smem_base, stream,
                args);
+    }
     return MAPF_OK;
 }
 

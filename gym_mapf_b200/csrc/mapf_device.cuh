@@ -49,6 +49,10 @@ struct Div32 {
 #define ENT_CORE(e) ((e) & 0x03ffffffffffffffull)  // without the parked bits
 // byte 6 of the entry (the pattern-row offset) from its high word, zero-extended: one PRMT
 __device__ __forceinline__ u32 ent_poff_hi(u32 ehi) { return __byte_perm(ehi, 0u, 0x4442); }
+// shared-window address of the entry's pattern row, `base + offset`, in ONE PRMT: the window address of the dynamic
+// shared memory is a multiple of 256 (checked at context creation) and the offset is below 256, so the sum is the
+// base with its low byte replaced
+__device__ __forceinline__ u32 ent_row(u32 ehi, u32 base) { return __byte_perm(ehi, base, 0x7652); }
 // destination of merged outcome j (0..2): bytes 2j, 2j+1 of the entry, zero-extended.  The upper two selector
 // nibbles 0xF replicate the (always clear) sign bit of byte 7.
 __device__ __forceinline__ u32 ent_dest(u64 e, u32 j) {
@@ -72,7 +76,10 @@ struct DevSpec {
     u64 nA;            // 5**n
     u64 smax[2];       // nS - 1
     FastDiv divLL;     // division by L*L
-    double invLL;      // 1 / (L*L)
+    // Exact floor divisions on the fp64 pipe (staged kernels only, see fdiv_floor()): reciprocals rounded UP and the
+    // matching constants -2**52 * reciprocal, plus the negated divisors for the one-IMAD remainders
+    double invLL_up, negcLL, invL_up, negcL;
+    u32 negLL, negL;
     // Two-word states: s = q * D + r with D = L**KLO(n) splits the digits into a low and a high group that are then
     // decoded independently with one-word arithmetic (split_ok: D < 2**63 and L**(n - KLO) < 2**49, so that one fp64
     // estimate of q is off by at most one).  Otherwise: long division over 32-bit limbs.
@@ -125,31 +132,44 @@ __device__ __forceinline__ void divmod_L(const DevSpec &sp, u32 x, u32 &q, u32 &
 // number of low digits of the two-word split for n agents: 2 * ceil(n / 4)
 #define MAPF_SPLIT_KLO(n) (2 * (((n) + 3) / 4))
 
+// floor(x / D) for an integer 0 <= x < 2**50 held as the double d = 2**52 + x (bit pattern: 0x43300000 | high word, low
+// word), on the otherwise idle fp64 pipe and with no correction step:
+//   t  = RU(d * inv_up - 2**52 * inv_up) = RU(x * inv_up)      one fused multiply-add, rounded up; inv_up = RU(1 / D)
+//   qd = RD(t + 2**52)                     = 2**52 + floor(t)    ulp is 1 in [2**52, 2**53)
+// x / D <= x * inv_up <= t < (x / D) * (1 + 2**-51), and the fraction of x / D is at most 1 - 1/D, so t stays below the
+// next integer whenever x < 2**50: floor(t) = floor(x / D).  The result is again "2**52 + q", ready for the next division.
+__device__ __forceinline__ double fdiv_floor(double d, double inv_up, double negc) {
+    return __dadd_rd(__fma_ru(d, inv_up, negc), 4503599627370496.0);
+}
+__device__ __forceinline__ double u32_as_biased_double(u32 x) { return __hiloint2double(0x43300000, (int)x); }
+
 // digits of a one-word value, two at a time: chunk = x mod L*L by one 64-bit magic division, then chunk / L
 template <int N, bool EXACT>
 __device__ __forceinline__ void decode_word(const DevSpec &sp, u64 x, int *cell) {
     constexpr int PAIRS = (N + 1) / 2;
     u32 chunk[PAIRS];
+    double chunk_d[PAIRS];  // EXACT: 2**52 + chunk where it fell out of a division for free (else unused)
+    bool have_d[PAIRS];
+#pragma unroll
+    for (int p = 0; p < PAIRS; ++p) have_d[p] = false;
 #pragma unroll
     for (int p = 0; p < PAIRS; ++p) {
         if (p + 1 < PAIRS) {
-            u64 q;
             if (EXACT && N - 2 * p <= 4) {
                 // At most four digits left and (guaranteed with EXACT, i.e. whenever the move table is staged in shared
-                // memory: L <= 5632) L**4 < 2**52, L*L < 2**31: the quotient comes from the
-                // otherwise idle fp64 pipe.  2**52 + x is the double whose mantissa is x, so x -> double is one add;
-                // the product with 1/(L*L) is within 2**-20 of x / (L*L), so rounding it to the nearest integer (one
-                // more add of 2**52) gives floor or floor + 1, and the sign of the remainder tells which.
-                const double d = __dadd_rn(__hiloint2double(0x43300000 | (int)(u32)(x >> 32), (int)(u32)x), -4503599627370496.0);
-                u32 qq = (u32)__double2loint(__dadd_rn(__dmul_rn(d, sp.invLL), 4503599627370496.0));
-                int r = (int)((u32)x - qq * sp.LL);
-                if (r < 0) { r += (int)sp.LL; qq -= 1u; }
-                chunk[p] = (u32)r;
-                q = qq;
-            } else {
-                q = fastdiv(x, sp.divLL);
-                chunk[p] = (u32)x - (u32)q * sp.LL;
+                // memory: L <= 5632) L**4 < 2**50: quotient on the fp64 pipe, remainder with one multiply-add.  This is
+                // the last division by L*L: the quotient is the top chunk.
+                const double d = __hiloint2double(0x43300000 | (int)(u32)(x >> 32), (int)(u32)x);
+                const double qd = fdiv_floor(d, sp.invLL_up, sp.negcLL);
+                const u32 qq = (u32)__double2loint(qd);
+                chunk[p] = (u32)x + qq * sp.negLL;
+                chunk[p + 1] = qq;
+                chunk_d[p + 1] = qd;
+                have_d[p + 1] = true;
+                break;
             }
+            const u64 q = fastdiv(x, sp.divLL);
+            chunk[p] = (u32)x - (u32)q * sp.LL;
             x = q;
         } else {
             chunk[p] = (u32)x;
@@ -159,7 +179,13 @@ __device__ __forceinline__ void decode_word(const DevSpec &sp, u64 x, int *cell)
     for (int p = 0; p < PAIRS; ++p) {
         if (2 * p + 1 < N) {
             u32 q, r;
-            divmod_L<EXACT>(sp, chunk[p], q, r);
+            if (EXACT) {  // chunk < L*L < 2**25
+                const double cd = have_d[p] ? chunk_d[p] : u32_as_biased_double(chunk[p]);
+                q = (u32)__double2loint(fdiv_floor(cd, sp.invL_up, sp.negcL));
+                r = chunk[p] + q * sp.negL;
+            } else {
+                divmod_L<EXACT>(sp, chunk[p], q, r);
+            }
             cell[2 * p] = (int)r;
             cell[2 * p + 1] = (int)q;
         } else {
@@ -291,7 +317,7 @@ __device__ __forceinline__ void decode_action(u32 a, int (&act)[N]) {
 // state: one 64/128-bit compare instead of one compare per agent)
 template <int N>
 __device__ __forceinline__ bool is_terminal(const DevSpec &sp, const int (&cell)[N], u64 lo, u64 hi) {
-    bool dup = false;
+    bool dup = false;  // (`||`: measured faster than a branch-free `|` chain, r02 ablations)
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -335,6 +361,7 @@ __device__ __forceinline__ int parked_agents(const DevSpec &sp, const int (&prev
 template <int N>
 __device__ __forceinline__ u32 parked_from_entries(const DevSpec &sp, u32 act0, const u32 (&ehi)[N], const int (&prev)[N],
                                                    const u32 (&actv)[N]) {
+    if (!sp.soc) return 0u;  // kernel-uniform: under Makespan every row of the reward table holds one value
     u32 bits = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {

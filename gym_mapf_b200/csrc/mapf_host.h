@@ -7,7 +7,8 @@ struct KernelSet {
     const void *step_philox1 = nullptr;  // k_step<N, W, LUTS, TAPE=false, EPT=1>
     const void *step_philox2 = nullptr;  // ... EPT=2 (128-bit I/O)
     const void *step_tape = nullptr;     // k_step<N, W, LUTS, TAPE=true, EPT=1>
-    const void *rollout_philox = nullptr, *rollout_tape = nullptr;
+    const void *rollout_philox = nullptr, *rollout_tape = nullptr;  // k_rollout<N, W, LUTS, TAPE, EPT=1>
+    const void *rollout_philox2 = nullptr;                            // ... EPT=2 (128-bit stores)
     const void *step_lanes_philox = nullptr, *step_lanes_tape = nullptr;  // k_step_lanes<N, TAPE>: 2..8 agents, one-word states
     const void *step_group_philox = nullptr, *step_group_tape = nullptr;  // k_step_group<N, W, TAPE>; staged move tables only
     const void *expand = nullptr, *expand_range = nullptr;

@@ -12,8 +12,9 @@ static void fill(KernelSet *k) {
     k->step_philox1 = (const void *)k_step<N, W, LUTS, false, 1>;
     k->step_philox2 = (const void *)k_step<N, W, LUTS, false, 2>;
     k->step_tape = (const void *)k_step<N, W, LUTS, true, 1>;
-    k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false>;
-    k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true>;
+    k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false, 1>;
+    if constexpr (N <= 6) k->rollout_philox2 = (const void *)k_rollout<N, W, LUTS, false, 2>;
+    k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true, 1>;
     if constexpr (LUTS && W == 1 && N >= 2 && N <= 8) {
         k->step_lanes_philox = (const void *)k_step_lanes<N, false>;
         k->step_lanes_tape = (const void *)k_step_lanes<N, true>;

@@ -12,6 +12,27 @@
 #ifndef MAPF_ABLATE
 #define MAPF_ABLATE 0  // timing experiments only (tools/sweep8.sh); 0 = the real kernel
 #endif
+// Timeline builds only (-DMAPF_TRACE, tools/trace_step.py): thread 0 of every CTA of the Philox-mode k_step stamps
+// %globaltimer at its phase boundaries into the buffer passed in place of the (unused) `uniforms` pointer:
+// buf[0] = next free slot; slot = {tag << 48 | (step & 0xffff) << 32 | smid << 16 | blockIdx, nanoseconds}.
+#ifdef MAPF_TRACE
+__device__ __forceinline__ void trace_stamp(const double *buf, u64 step, u32 tag) {
+    if (threadIdx.x != 0 || buf == nullptr) return;
+    u64 *b = reinterpret_cast<u64 *>(const_cast<double *>(buf));
+    u64 t;
+    u32 smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const u64 slot = atomicAdd(reinterpret_cast<unsigned long long *>(b), 1ull);
+    if (slot < (1ull << 20)) {
+        b[2 + 2 * slot] = ((u64)tag << 48) | ((step & 0xffffull) << 32) | ((u64)smid << 16) | (u64)blockIdx.x;
+        b[3 + 2 * slot] = t;
+    }
+}
+#define TRACE(tag) trace_stamp(uniforms, step, tag)
+#else
+#define TRACE(tag)
+#endif
 #ifndef MAPF_PREFETCH_ITEMS
 #define MAPF_PREFETCH_ITEMS 1
 #endif
@@ -1010,8 +1031,10 @@ struct EnvIn {
 struct EnvOut {
     u64 lo, hi;
     double reward, prob;
-    u32 done, coll;
+    u32 kind;  // 0 living, 1 clash, 2 goal, 3 step from a terminal state: done = kind != 0, collision = kind == 1
 };
+__device__ __forceinline__ u32 out_done(const EnvOut &o) { return o.kind != 0u ? 1u : 0u; }
+__device__ __forceinline__ u32 out_coll(const EnvOut &o) { return o.kind == 1u ? 1u : 0u; }
 
 template <int N>
 __device__ __forceinline__ void env_draws(const PhiloxKeys &K, u64 env, u64 step, EnvIn<N> &in) {
@@ -1042,7 +1065,7 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
         const u64 e = lut_entry<LUTS>(tb, (u32)in.cell[i], in.actv[i]);
 #endif
         ehi[i] = (u32)(e >> 32);
-        const u32 row = tb.base + ent_poff_hi(ehi[i]);
+        const u32 row = ent_row(ehi[i], tb.base);
         u32 pick;
         if (TAPE) {
             const double ui = u[i];
@@ -1071,14 +1094,13 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
     out.reward = lds_f64<MAPF_SMEM_REW>(
         tb.base + ((u32)(kind * MAPF_REW_STRIDE) + parked_from_entries<N>(sp, tb.act0, ehi, in.cell, in.actv)) * 8u);
     out.prob = total;
-    out.done = kind != 0 ? 1u : 0u;
-    out.coll = kind == 1 ? 1u : 0u;
+    out.kind = (u32)kind;
     if (term) {
         out.lo = in.lo; out.hi = in.hi;
 #pragma unroll
         for (int i = 0; i < N; ++i) nxt[i] = in.cell[i];
     }
-    if ((opts & 1u) && out.done) {  // MAPF_OPT_AUTO_RESET
+    if ((opts & 1u) && kind != 0) {  // MAPF_OPT_AUTO_RESET
         out.lo = sp.s0[0]; out.hi = sp.s0[1];
 #pragma unroll
         for (int i = 0; i < N; ++i) nxt[i] = (int)sp.start[i];
@@ -1117,6 +1139,70 @@ __device__ __forceinline__ void load_raw(const u64 *states, const int *__restric
     }
 }
 
+// One item (EPT consecutive envs) of k_step: decode, sample, judge, store.  `raw` / `draws` were fetched / generated one
+// iteration ahead by the caller.
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
+__device__ __forceinline__ void step_item(const DevSpec &sp, const SmemTables &tb, u32 it,
+                                          const RawIn<WORDS, EPT> &raw, const u32 (&draws)[EPT][((N + 3) / 4) * 4],
+                                          const double *__restrict__ uniforms, u32 opts, u64 *next_states,
+                                          double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done,
+                                          u8 *__restrict__ coll) {
+    constexpr int NW = ((N + 3) / 4) * 4;
+    EnvIn<N> in[EPT];
+    const u32 b = it * EPT;
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        in[q].lo = raw.lo[q];
+        in[q].hi = raw.hi[q];
+        if (!TAPE) {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) in[q].w[j] = draws[q][j];
+        }
+        decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
+    }
+    EnvOut o[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        load_actions<N>(sp, tb, raw.a[q], in[q].actv);
+        int nxt[N];
+        o[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (size_t)(b + q) * N : nullptr, opts, nxt);
+    }
+#if MAPF_ABLATE == 3  // experiment: almost no stores (the condition is never true, but the compiler cannot know)
+    if (o[0].prob < -1.0)
+#endif
+    if (EPT == 2) {
+        if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
+        else {
+            store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
+            store_state<WORDS>(next_states, b + 1, o[EPT - 1].lo, o[EPT - 1].hi);
+        }
+        reinterpret_cast<double2 *>(reward)[it] = make_double2(o[0].reward, o[EPT - 1].reward);
+        reinterpret_cast<double2 *>(prob)[it] = make_double2(o[0].prob, o[EPT - 1].prob);
+        // both flag bytes of both envs from two byte permutes: byte `kind` of 0x01010100 is done, of 0x00000100 collision
+        const u32 sel = o[0].kind | (o[EPT - 1].kind << 4);
+        reinterpret_cast<u16 *>(done)[it] = (u16)__byte_perm(0x01010100u, 0u, sel);
+        reinterpret_cast<u16 *>(coll)[it] = (u16)__byte_perm(0x00000100u, 0u, sel);
+    } else {
+        store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
+        reward[b] = o[0].reward;
+        prob[b] = o[0].prob;
+        done[b] = (u8)out_done(o[0]);
+        coll[b] = (u8)out_coll(o[0]);
+    }
+}
+
+template <int N, int EPT>
+__device__ __forceinline__ void item_draws(const PhiloxKeys &keys, u64 env0, u64 step, u32 it,
+                                           u32 (&draws)[EPT][((N + 3) / 4) * 4]) {
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+        EnvIn<N> tmp;
+        env_draws<N>(keys, env0 + (u64)(it * EPT + q), step, tmp);
+#pragma unroll
+        for (int j = 0; j < ((N + 3) / 4) * 4; ++j) draws[q][j] = tmp.w[j];
+    }
+}
+
 template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
 k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
@@ -1125,137 +1211,147 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
     extern __shared__ __align__(16) unsigned char smem[];
     // Programmatic dependent launch: let the next kernel of the stream start its prologue (table staging) while
     // this grid drains, and do our own prologue before waiting for the previous grid's results to be visible.
+    TRACE(0);
     asm volatile("griddepcontrol.launch_dependents;");
     SmemTables tb = tables_begin<LUTS>(sp, smem);
-    bool ready = false;
+    TRACE(1);
     const u32 n_items = B / EPT;
     const u32 stride = gridDim.x * blockDim.x;
     u32 it = blockIdx.x * blockDim.x + threadIdx.x;
     // The slip draws depend on nothing but (seed, env, step): those of the first item are generated BEFORE the wait
     // on the previous grid (they overlap its tail and the first DRAM round trip), those of every later item at the
-    // end of the iteration before it.
+    // end of the iteration before it.  The prefetched inputs are double-buffered (A / B) and the loop body is written
+    // out twice, so that "next" becomes "current" by renaming instead of by register moves.
     constexpr int NW = ((N + 3) / 4) * 4;
     u32 draws[EPT][NW];
-    if (!TAPE && it < n_items) {
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            EnvIn<N> tmp;
-            env_draws<N>(keys, env0 + (u64)(it * EPT + q), step, tmp);
-#pragma unroll
-            for (int j = 0; j < NW; ++j) draws[q][j] = tmp.w[j];
-        }
-    }
+    if (!TAPE && it < n_items) item_draws<N, EPT>(keys, env0, step, it, draws);
     // pull this thread's input lines towards L2 while the previous grid drains (a prefetch cannot observe stale
     // data: the loads below are issued after the wait); at most MAPF_PREFETCH_ITEMS grid-stride items ahead
     for (u32 pf = it, k = 0; pf < n_items && k < MAPF_PREFETCH_ITEMS; pf += stride, ++k) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const unsigned char *>(states) + (size_t)pf * EPT * WORDS * 8));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + (size_t)pf * EPT));
     }
+    TRACE(2);
+#ifndef MAPF_NO_GRID_WAIT  // experiment builds only: launches whose inputs do not depend on the previous launch
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    TRACE(3);
     RawIn<WORDS, EPT> raw;
     if (it < n_items) load_raw<WORDS, EPT>(states, actions, it, raw);
+    // the image was requested at kernel entry: wait for it here, before the loop, not inside its first iteration
+    // (measured: 10.00 -> 9.91 us per 2**20-env launch)
+    tables_wait<LUTS>(smem);
+#ifdef MAPF_TRACE
+    u32 trace_iter = 0;
+#endif
     while (it < n_items) {
-        EnvIn<N> in[EPT];
-        const u32 b = it * EPT;
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            in[q].lo = raw.lo[q];
-            in[q].hi = raw.hi[q];
-            if (!TAPE) {
-#pragma unroll
-                for (int j = 0; j < NW; ++j) in[q].w[j] = draws[q][j];
-            }
-        }
-        const u32 a_raw[2] = {raw.a[0], raw.a[EPT - 1]};
+        const RawIn<WORDS, EPT> cur = raw;
         const u32 it_next = it + stride;
-#if MAPF_ABLATE == 4  // experiment: no global loads after the first
-        if (it_next < n_items) { raw.lo[0] += it_next; raw.lo[EPT - 1] += 2 * it_next; raw.a[0] = (raw.a[0] + 7u) % 625u; }
-#else
         if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
+        step_item<N, WORDS, LUTS, TAPE, EPT>(sp, tb, it, cur, draws, uniforms, opts, next_states, reward, prob, done, coll);
+#ifdef MAPF_TRACE
+        if (trace_iter == 0) TRACE(4);
+        TRACE(8 + trace_iter);
+        ++trace_iter;
 #endif
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
-        }
-        if (!ready) { tables_wait<LUTS>(smem); ready = true; }
-        EnvOut o[EPT];
-#pragma unroll
-        for (int q = 0; q < EPT; ++q) {
-            load_actions<N>(sp, tb, a_raw[q], in[q].actv);
-            int nxt[N];
-            o[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (size_t)(b + q) * N : nullptr, opts,
-                                                  nxt);
-        }
-#if MAPF_ABLATE == 3  // experiment: almost no stores (the condition is never true, but the compiler cannot know)
-        if (o[0].prob < -1.0)
-#endif
-        if (EPT == 2) {
-            if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
-            else {
-                store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
-                store_state<WORDS>(next_states, b + 1, o[EPT - 1].lo, o[EPT - 1].hi);
-            }
-            reinterpret_cast<double2 *>(reward)[it] = make_double2(o[0].reward, o[EPT - 1].reward);
-            reinterpret_cast<double2 *>(prob)[it] = make_double2(o[0].prob, o[EPT - 1].prob);
-            reinterpret_cast<u16 *>(done)[it] = (u16)(o[0].done | (o[EPT - 1].done << 8));
-            reinterpret_cast<u16 *>(coll)[it] = (u16)(o[0].coll | (o[EPT - 1].coll << 8));
-        } else {
-            store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
-            reward[b] = o[0].reward;
-            prob[b] = o[0].prob;
-            done[b] = (u8)o[0].done;
-            coll[b] = (u8)o[0].coll;
-        }
-        if (!TAPE && it_next < n_items) {
-#pragma unroll
-            for (int q = 0; q < EPT; ++q) {
-                EnvIn<N> tmp;
-                env_draws<N>(keys, env0 + (u64)(it_next * EPT + q), step, tmp);
-#pragma unroll
-                for (int j = 0; j < NW; ++j) draws[q][j] = tmp.w[j];
-            }
-        }
+        if (!TAPE && it_next < n_items) item_draws<N, EPT>(keys, env0, step, it_next, draws);
         it = it_next;
     }
-    if (!ready) tables_wait<LUTS>(smem);
+    TRACE(7);
 }
 
-// T steps per launch; the env's cells stay in registers between steps, each step's results go to slab t.
-template <int N, int WORDS, bool LUTS, bool TAPE>
-__global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
+// T steps per launch; the env's cells stay in registers between steps (no state read, no decode after the first step),
+// each step's results go to slab t of the [T, B] outputs: W + 18 bytes written per env-step (+ 4 read when the actions
+// are given).  EPT = 2: a thread owns two neighbouring envs and writes their results with 128-bit stores, exactly as
+// k_step does; the actions of step t + 1 are loaded, and its slip draws generated, while step t is computed.
+// (two envs carried in registers across steps want ~110 registers: the EPT = 2 kernel runs ONE 512-thread CTA per SM.
+// Measured on 2**20 C2 envs, T = 32, actions given: 512 x 1 9.42 us per step, 256 x 2 9.85, 256 x 3 (80 registers) 10.68 --
+// with 512 threads per SM every thread owns 6.92 env pairs, 98.8 % of 7 full rounds; 768 threads leave 4.61 of 5.)
+#ifndef MAPF_ROLLOUT2_THREADS
+#define MAPF_ROLLOUT2_THREADS 512
+#endif
+#ifndef MAPF_ROLLOUT2_BLOCKS
+#define MAPF_ROLLOUT2_BLOCKS(N) 1
+#endif
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
+__global__ void __launch_bounds__((EPT == 2 ? MAPF_ROLLOUT2_THREADS : MAPF_MAX_THREADS),
+                                   (EPT == 2 ? MAPF_ROLLOUT2_BLOCKS(N) : MAPF_MIN_BLOCKS(N)))
 k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ actions, i64 T, u32 B,
           const double *__restrict__ uniforms, u64 step0, u64 env0, u32 opts, u64 *__restrict__ next_states,
           double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int NW = ((N + 3) / 4) * 4;
     SmemTables tb = tables_begin<LUTS>(sp, smem);
+    const u32 n_items = B / EPT;  // the launcher picks EPT = 2 only for even B
     bool ready = false;
-    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-        EnvIn<N> in;
-        load_state<WORDS>(states, b, in.lo, in.hi);
-        decode_state<N, WORDS, LUTS>(sp, in.lo, in.hi, in.cell);
-        for (i64 t = 0; t < T; ++t) {
-            const i64 o = t * (i64)B + b;
-            const u64 env = env0 + (u64)b, stp = step0 + (u64)t;
-            const u32 a = actions ? (u32)actions[o] : random_action(sp, keys, env, stp);
-            if (!TAPE) env_draws<N>(keys, env, stp, in);
-            if (!ready) { tables_wait<LUTS>(smem); ready = true; }
-            load_actions<N>(sp, tb, a, in.actv);
-            int nxt[N];
-            EnvOut r = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in, TAPE ? uniforms + o * N : nullptr, opts, nxt);
-            store_state<WORDS>(next_states, o, r.lo, r.hi);
-            reward[o] = r.reward;
-            prob[o] = r.prob;
-            done[o] = (u8)r.done;
-            coll[o] = (u8)r.coll;
-            // carry the env forward in registers (cells of the possibly reset next state)
-            in.lo = r.lo;
-            in.hi = r.hi;
+    for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        EnvIn<N> in[EPT];
+        const u32 b = it * EPT;
+        u32 a_next[EPT];
 #pragma unroll
-            for (int i = 0; i < N; ++i) in.cell[i] = nxt[i];
+        for (int q = 0; q < EPT; ++q) {
+            load_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
+            a_next[q] = actions ? (u32)actions[b + q] : 0u;
+            if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step0, in[q]);
         }
-        store_state<WORDS>(states, b, in.lo, in.hi);
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
+        if (!ready) { tables_wait<LUTS>(smem); ready = true; }
+        for (i64 t = 0; t < T; ++t) {
+            const u64 stp = step0 + (u64)t;
+            const size_t o = (size_t)t * B + b;   // env-major position inside slab t
+            const size_t ov = (size_t)t * n_items + it;  // the same in units of EPT envs
+            u32 a_cur[EPT];
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) a_cur[q] = actions ? a_next[q] : random_action(sp, keys, env0 + (u64)(b + q), stp);
+            if (actions && t + 1 < T) {  // in flight during the compute below
+                if (EPT == 2) {
+                    const int2 a2 = *reinterpret_cast<const int2 *>(actions + o + B);
+                    a_next[0] = (u32)a2.x; a_next[EPT - 1] = (u32)a2.y;
+                } else {
+                    a_next[0] = (u32)actions[o + B];
+                }
+            }
+            EnvOut r[EPT];
+            int nxt[EPT][N];
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) {
+                load_actions<N>(sp, tb, a_cur[q], in[q].actv);
+                r[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (o + q) * N : nullptr, opts, nxt[q]);
+            }
+            if (EPT == 2) {
+                if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[ov] = make_ulonglong2(r[0].lo, r[EPT - 1].lo);
+                else {
+                    store_state<WORDS>(next_states, o, r[0].lo, r[0].hi);
+                    store_state<WORDS>(next_states, o + 1, r[EPT - 1].lo, r[EPT - 1].hi);
+                }
+                reinterpret_cast<double2 *>(reward)[ov] = make_double2(r[0].reward, r[EPT - 1].reward);
+                reinterpret_cast<double2 *>(prob)[ov] = make_double2(r[0].prob, r[EPT - 1].prob);
+                const u32 sel = r[0].kind | (r[EPT - 1].kind << 4);  // see step_item()
+                reinterpret_cast<u16 *>(done)[ov] = (u16)__byte_perm(0x01010100u, 0u, sel);
+                reinterpret_cast<u16 *>(coll)[ov] = (u16)__byte_perm(0x00000100u, 0u, sel);
+            } else {
+                store_state<WORDS>(next_states, o, r[0].lo, r[0].hi);
+                reward[o] = r[0].reward;
+                prob[o] = r[0].prob;
+                done[o] = (u8)out_done(r[0]);
+                coll[o] = (u8)out_coll(r[0]);
+            }
+            // carry the envs forward in registers (cells of the possibly reset next state); next step's draws
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) {
+                in[q].lo = r[q].lo;
+                in[q].hi = r[q].hi;
+#pragma unroll
+                for (int i = 0; i < N; ++i) in[q].cell[i] = nxt[q][i];
+                if (!TAPE && t + 1 < T) env_draws<N>(keys, env0 + (u64)(b + q), stp + 1, in[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < EPT; ++q) store_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
     }
     if (!ready) tables_wait<LUTS>(smem);
+    (void)NW;
 }
 
 // =====================================================================================================
@@ -1378,8 +1474,8 @@ k_step_group(const DevSpec *__restrict__ specs, const u32 *__restrict__ seg_begi
             store_state<WORDS>(next_states, i, o.lo, o.hi);
             reward[i] = o.reward;
             prob[i] = o.prob;
-            done[i] = (u8)o.done;
-            coll[i] = (u8)o.coll;
+            done[i] = (u8)out_done(o);
+            coll[i] = (u8)out_coll(o);
             if (!TAPE && i_next < hi) {
                 EnvIn<N> tmp;
                 env_draws<N>(keys, env0 + (u64)i_next, step, tmp);
@@ -1497,7 +1593,7 @@ k_step_lanes(DevSpec sp, LaneConsts lc, PhiloxKeys keys, const u64 *states, cons
             if (li == (u32)(G - 1)) qan = 0u;
             const u32 act = active ? qa - qan * 5u : 0u;
             const u64 e = lds_u64<0>(tb.lut + (active ? cell : 0u) * 40u + act * 8u);
-            const u32 row = tb.base + ent_poff_hi((u32)(e >> 32));
+            const u32 row = ent_row((u32)(e >> 32), tb.base);
             u32 pick;
             if (TAPE) {
                 const u32 bj = rd * 32u + gbase + (u32)j;

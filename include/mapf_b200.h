@@ -52,8 +52,13 @@ enum { MAPF_FLAG_DONE = 1, MAPF_FLAG_COLLISION = 2, MAPF_FLAG_TERMINAL = 4 };
 
 /* step / rollout option bits */
 enum {
-    MAPF_OPT_AUTO_RESET = 1 /* an env whose step returned done is put back on the start state (next_state holds
-                               the start state for it); off = the reference's semantics (mapf_env.py:237-266) */
+    MAPF_OPT_AUTO_RESET = 1, /* an env whose step returned done is put back on the start state (next_state holds
+                                the start state for it); off = the reference's semantics (mapf_env.py:237-266) */
+    MAPF_OPT_SHARE_SM = 2    /* mapf_step only: launch ONE resident CTA per SM instead of filling the GPU.  For callers
+                                that keep their envs in two independent pools and step each pool on its own stream
+                                (every pool is a chain of dependent launches, mapf_env.py:237-266 called once per env
+                                and step): the two chains then share every SM, and the drain / fill of one pool's
+                                launch boundary is covered by the other pool's compute.  Results are identical. */
 };
 
 /* Everything MapfEnv.__init__ receives (mapf_env.py:116-125); all HOST memory, copied by mapf_ctx_create. */

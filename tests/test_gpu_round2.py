@@ -148,9 +148,9 @@ def test_bench_checker_on_small_cases(torch):
     sys.path.insert(0, ROOT)
     import bench
     from tools import bench_configs
-    cases = bench_configs.run_all(0, 1, 0, only={"c2_step_strong", "c3_table", "c4_step", "c2_expand", "c2_rollout", "c5_n2",
-                                                 "c5_n8", "c5_density_w2"}, quick=True)
-    assert len(cases) == 8
+    cases = bench_configs.run_all(0, 1, 0, only={"c2_step_strong", "c3_table", "c4_step", "c2_expand", "c2_rollout",
+                                                 "c2_rollout_random", "c5_n2", "c5_n8", "c5_density_w2"}, quick=True)
+    assert len(cases) == 9
     for name, entry, payload in cases:
         ok, what = bench.verify_payload(payload)
         assert ok, (name, what)

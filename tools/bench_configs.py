@@ -245,30 +245,37 @@ def step_case(tag, env, soc, dev, peak, B, world, rank, ring, K, graph, seed=77,
     return entry, payload
 
 
-def rollout_case(tag, env, soc, dev, peak, B, T, seed=5, sample=4096):
+def rollout_case(tag, env, soc, dev, peak, B, T, seed=5, sample=4096, given_actions=True):
+    """T steps per launch.  `given_actions`: the policy's actions are an input, int32[T, B] (W + 18 bytes written + 4 read
+    per env-step); otherwise a uniformly random policy is drawn on the device (one more Philox block per env-step)."""
     eng = env.engine
     W = eng.words * 8
     states0 = eng.states_from_ints([eng.s0]).expand(*eng.state_shape(B)).contiguous()
     states = states0.clone()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    actions = torch.randint(0, env.nA, (T, B), generator=g, device=dev, dtype=torch.int32) if given_actions else None
     out = (torch.empty((T,) + eng.state_shape(B), dtype=torch.int64, device=dev),
            torch.empty((T, B), dtype=torch.float64, device=dev), torch.empty((T, B), dtype=torch.float64, device=dev),
            torch.empty((T, B), dtype=torch.bool, device=dev), torch.empty((T, B), dtype=torch.bool, device=dev))
-
-    t = timed(lambda: eng.rollout(states, None, T, seed=seed, step_index=0, auto_reset=True, out=out), reps=5, warm=1) / T
+    t = timed(lambda: eng.rollout(states, actions, T, seed=seed, step_index=0, auto_reset=True, out=out), reps=5, warm=1) / T
     states.copy_(states0)  # the sampled call starts from known states
-    eng.rollout(states, None, T, seed=seed, step_index=0, auto_reset=True, out=out)
-    by = B * (W + 18)
+    eng.rollout(states, actions, T, seed=seed, step_index=0, auto_reset=True, out=out)
+    per = W + 18 + (4 if given_actions else 0)
+    by = B * per
     m = min(sample, B)
     s_lo, s_hi = split_np(eng, states0[:m])
     n_lo, n_hi = split_np(eng, out[0][:, :m].contiguous().reshape((T * m,) + ((2,) if eng.words == 2 else ())))
     payload = {"kind": "rollout", "spec": spec_of(env, soc), "s_lo": s_lo, "s_hi": s_hi, "seed": seed, "step_index": 0,
                "env_offset": 0, "T": T, "s0": int(eng.s0), "nA": int(eng.nA), "next_lo": n_lo.reshape(T, m),
+               "actions": None if actions is None else actions[:, :m].cpu().numpy().astype(np.int64),
                "next_hi": n_hi.reshape(T, m), "reward": out[1][:, :m].cpu().numpy(), "prob": out[2][:, :m].cpu().numpy(),
                "done": out[3][:, :m].cpu().numpy().astype(np.uint8), "collision": out[4][:, :m].cpu().numpy().astype(np.uint8)}
     entry = {"workload": tag, "kernel": "k_rollout", "unit": "transitions/s", "n_agents": eng.n, "state_bytes": W,
-             "envs": B, "T": T, "us_per_step": t * 1e6, "value": B / t, "bytes_per_unit": W + 18, "gbs": by / t / 1e9,
-             "frac": by / t / 1e9 / peak, "policy": "random actions drawn on the device (Philox block 15)"}
-    del out
+             "envs": B, "T": T, "us_per_step": t * 1e6, "value": B / t, "bytes_per_unit": per, "gbs": by / t / 1e9,
+             "frac": by / t / 1e9 / peak,
+             "policy": "actions given, int32[T, B]" if given_actions else "random actions drawn on the device (Philox block 15)"}
+    del out, actions
     return entry, payload
 
 
@@ -367,8 +374,13 @@ def run_all(device_index, world, rank, only=None, quick=False):
     add("c1", lambda: c1_case(dev, peak, device_index))
     add("c2_expand", lambda: expand_case("C2 expand: room-32-32-4 scen 1, 4 agents, SoC; random (s, a) rows",
                                          make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, target, 2))
-    add("c2_rollout", lambda: rollout_case("C2 rollout: room-32-32-4 scen 1, 4 agents, SoC; 32 steps per launch",
-                                           make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, 1 << 20, 32))
+    add("c2_rollout", lambda: rollout_case("C2 rollout: room-32-32-4 scen 1, 4 agents, SoC; 32 steps per launch, actions given",
+                                           make("room-32-32-4", 1, 4, True, device_index), True, dev, peak,
+                                           (1 << 18) if quick else (1 << 20), 32))
+    add("c2_rollout_random", lambda: rollout_case(
+        "C2 rollout: room-32-32-4 scen 1, 4 agents, SoC; 32 steps per launch, random policy drawn on the device",
+        make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, (1 << 18) if quick else (1 << 20), 32,
+        given_actions=False))
     for n in range(2, 11):
         add("c5_n%d" % n, lambda n=n: expand_case("C5 expand: empty-32-32 scen 1, %d agents, SoC; random (s, a) rows" % n,
                                                   make("empty-32-32", 1, n, True, device_index), True, dev, peak, target,

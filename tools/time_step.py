@@ -35,10 +35,29 @@ def main():
     K = 96
     use_graph = os.environ.get("TIME_GRAPH", "0") == "1"
 
+    n_streams = int(os.environ.get("TIME_STREAMS", "1"))
+    pools = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else []
+    H = B // max(n_streams, 1)
+
     def run_k():
+        if not pools:
+            for i in range(K):
+                j = i % R
+                eng.step(states[j], actions[j], seed=3, step_index=100 + i, auto_reset=True, out=outs[j])
+            return
+        # the batch as `n_streams` independent env pools, each stepped on its own stream (a chain of dependent launches)
+        cur = torch.cuda.current_stream()
+        for st in pools:
+            st.wait_stream(cur)
         for i in range(K):
             j = i % R
-            eng.step(states[j], actions[j], seed=3, step_index=100 + i, auto_reset=True, out=outs[j])
+            for k, st in enumerate(pools):
+                with torch.cuda.stream(st):
+                    sl = slice(k * H, (k + 1) * H)
+                    eng.step(states[j][sl], actions[j][sl], seed=3, step_index=100 + i, env_offset=k * H, auto_reset=True,
+                             out=tuple(t[sl] for t in outs[j]), share_sm=os.environ.get("TIME_SHARE_SM", "1") == "1")
+        for st in pools:
+            cur.wait_stream(st)
 
     graph = None
     if use_graph:
