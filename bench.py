@@ -575,8 +575,10 @@ def run_ours(args):
             with open(ceil_path) as f:
                 ceil = json.load(f).get(str(world))
             if ceil:
-                e2e["pcie_ceiling_gbs"] = ceil
-                e2e["pcie_frac"] = e2e["host_link_gbs"] / ceil["both_total_gbs"]
+                e2e["pcie_ceiling"] = {"step_mix_total_gbs": ceil["step_mix_total_gbs"], "both_total_gbs": ceil["both_total_gbs"],
+                                       "source": "profiles/r02_pcie_ceiling.json (tools/pcie_peak.py: %d GPUs copying "
+                                                 "concurrently, pinned memory, 12 : 26 byte in / out mix)" % world}
+                e2e["pcie_frac"] = e2e["host_link_gbs"] / ceil["step_mix_total_gbs"]
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)
 
