@@ -39,10 +39,28 @@ def main():
         if j + 1 < R:
             states.append(out[0].clone())
 
+    n_pools = int(os.environ.get("TIME_STREAMS", "1"))
+    pools = [torch.cuda.Stream() for _ in range(n_pools)] if n_pools > 1 else []
+    H = B // max(n_pools, 1)
+
     def run_k():
+        if not pools:
+            for i in range(K):
+                j = i % R
+                eng.step(states[j], actions[j], seed=3, step_index=100 + i, auto_reset=True, out=outs[j])
+            return
+        cur = torch.cuda.current_stream()
+        for st in pools:
+            st.wait_stream(cur)
         for i in range(K):
             j = i % R
-            eng.step(states[j], actions[j], seed=3, step_index=100 + i, auto_reset=True, out=outs[j])
+            for k, st in enumerate(pools):  # pool k stamps its launches with step index 100 + i + 1000 * k
+                with torch.cuda.stream(st):
+                    sl = slice(k * H, (k + 1) * H)
+                    eng.step(states[j][sl], actions[j][sl], seed=3, step_index=100 + i + 1000 * k, env_offset=k * H,
+                             auto_reset=True, out=tuple(t[sl] for t in outs[j]), share_sm=True)
+        for st in pools:
+            cur.wait_stream(st)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -67,8 +85,10 @@ def main():
         ((ev[:, 0] >> 16) & 0xffff).astype(int), (ev[:, 0] & 0xffff).astype(int), ev[:, 1].astype(np.int64)
     t0 = t.min()
     t = (t - t0) / 1e3  # us
-    print("# graph of %d launches of k_step<4,...> over %d envs each: %.2f us per launch by CUDA events (with the stamps)" % (
-        K, B, e0.elapsed_time(e1) * 1e3 / K))
+    print("# graph of %d steps of k_step<4,...> over %d envs, %d pool(s): %.2f us per step by CUDA events (with the stamps; "
+          "the stamps' atomics cost ~40 %%)" % (K, B, max(n_pools, 1), e0.elapsed_time(e1) * 1e3 / K))
+    if n_pools > 1:
+        print("# launch ids: pool 0 = 0..%d, pool 1 = 1000.. (sorted by id, not by time: compare the two pools' columns)" % (K - 1))
     print("# %d stamps; columns are microseconds since the first stamp: min / median / max over the launch's CTAs" % n)
     print("# launch | CTA entry            | wait released        | tables ready (1st it) | end of iteration 1   | CTA exit             | "
           "span first entry -> last exit | next launch's first entry - this launch's last exit")
