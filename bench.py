@@ -570,6 +570,19 @@ def run_ours(args):
                "api": "mapf_step_host (C ABI, pinned host buffers in and out)",
                "host_numa_bind": prev_affinity is not None,
                "host_link_gbs": world * B * 38 * n_e2e / dt / 1e9}
+        # opt-in compact result layout (MAPF_OPT_COMPACT: reward code + one flag byte, 18 instead of 26 B/env back)
+        cout = (hout[0], torch.empty(B, dtype=torch.uint8).pin_memory(), hout[2], torch.empty(B, dtype=torch.uint8).pin_memory())
+        for i in range(3):
+            eng.step_host(hs, ha, cout, seed=seed, step_index=i, env_offset=env_offset, auto_reset=True, compact=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            eng.step_host(hs, ha, cout, seed=seed, step_index=10 + i, env_offset=env_offset, auto_reset=True, compact=True)
+        torch.cuda.synchronize()
+        dtc = max_ranks(time.perf_counter() - t0)
+        e2e["compact"] = {"value": world * B * n_e2e / dtc, "unit": "transitions/s", "h2d_bytes_per_step": B * 12 * world,
+                          "d2h_bytes_per_step": B * 18 * world, "host_link_gbs": world * B * 30 * n_e2e / dtc / 1e9,
+                          "api": "mapf_step_host with MAPF_OPT_COMPACT (reward = reward_table[code], flags = done | collision << 1)"}
         ceil_path = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
         if os.path.exists(ceil_path):  # measured PCIe ceilings of this pool's boxes (tools/pcie_peak.py), if committed
             with open(ceil_path) as f:

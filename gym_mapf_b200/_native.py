@@ -15,9 +15,10 @@ MAPF_OK, MAPF_ERR_INVALID, MAPF_ERR_KEY, MAPF_ERR_UNSUPPORTED, MAPF_ERR_CUDA, MA
 MAPF_SOC, MAPF_MAKESPAN = 0, 1
 OPT_AUTO_RESET = 1
 OPT_SHARE_SM = 2
+OPT_COMPACT = 4
 FLAG_DONE, FLAG_COLLISION = 1, 2
 
-EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_decode_states",
+EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_ctx_reward_table", "mapf_decode_states",
            "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_count_scan_rows",
            "mapf_count_scan_range", "mapf_expand",
            "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_step_lanes", "mapf_rollout", "mapf_step_host",
@@ -78,6 +79,7 @@ def lib():
         L.mapf_ctx_destroy.restype = None
         L.mapf_ctx_info.argtypes = [vp, C.POINTER(MapfInfo)]
         L.mapf_ctx_moves.argtypes = [vp, vp, vp, vp, vp]
+        L.mapf_ctx_reward_table.argtypes = [vp, vp]
         L.mapf_decode_states.argtypes = [vp, vp, i64, vp, vp]
         L.mapf_encode_states.argtypes = [vp, vp, i64, vp, vp]
         L.mapf_count_rows.argtypes = [vp, vp, vp, i64, vp, vp]
@@ -364,12 +366,15 @@ class Engine:
 
     # ---- step / rollout
     def step(self, states, actions, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False, out=None,
-             mapping="thread", share_sm=False):
+             mapping="thread", share_sm=False, compact=False):
         """`mapping`: "thread" (one thread per env, the shipped kernel) or "lanes" (one warp lane per agent, the measured
         alternative; 2..8 agents, one-word states).  `share_sm`: one resident CTA per SM (MAPF_OPT_SHARE_SM), for env
-        pools that are stepped concurrently on separate streams."""
+        pools that are stepped concurrently on separate streams.  `compact` (MAPF_OPT_COMPACT): the result is
+        (next_states, reward_code u8[B], prob, flags u8[B]) -- reward = reward_table()[code], flags = done | collision << 1."""
         B = states.shape[0]
         self._check_batch(states, actions, uniforms)
+        if compact:
+            return self._step_compact(states, actions, uniforms, seed, step_index, env_offset, auto_reset, out, share_sm)
         if out is None:
             import torch
             dev = self.torch_device
@@ -385,6 +390,27 @@ class Engine:
                 done.data_ptr(), coll.data_ptr(), self._stream())
         if rc:
             check(rc)
+        return out
+
+    def reward_table(self):
+        """f64[64]: every reward a step can return, indexed by the code of the compact result layout."""
+        if getattr(self, "_reward_table", None) is None:
+            t = np.zeros(64, np.float64)
+            check(lib().mapf_ctx_reward_table(self._h, _ptr(t)))
+            self._reward_table = t
+        return self._reward_table
+
+    def _step_compact(self, states, actions, uniforms, seed, step_index, env_offset, auto_reset, out, share_sm):
+        import torch
+        B, dev = states.shape[0], self.torch_device
+        if out is None:
+            out = (self.new_states(B), torch.empty(B, dtype=torch.uint8, device=dev),
+                   torch.empty(B, dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.uint8, device=dev))
+        ns, code, prob, flags = out
+        opts = OPT_COMPACT | (OPT_AUTO_RESET if auto_reset else 0) | (OPT_SHARE_SM if share_sm else 0)
+        check(self._mapf_step(self._h, states.data_ptr(), actions.data_ptr(), B,
+                              None if uniforms is None else uniforms.data_ptr(), seed, step_index, env_offset, opts,
+                              ns.data_ptr(), code.data_ptr(), prob.data_ptr(), flags.data_ptr(), None, self._stream()))
         return out
 
     def rollout(self, states, actions, T, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=True, out=None):
@@ -406,10 +432,18 @@ class Engine:
                                  _ptr(done), _ptr(coll), self._stream()))
         return out
 
-    def step_host(self, states, actions, out, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False):
-        """Host-buffer step (numpy arrays or pinned CPU tensors in, the five results written into `out`)."""
-        ns, reward, prob, done, coll = out
+    def step_host(self, states, actions, out, uniforms=None, seed=0, step_index=0, env_offset=0, auto_reset=False,
+                  compact=False):
+        """Host-buffer step (numpy arrays or pinned CPU tensors in, the five results written into `out`).  `compact`:
+        `out` = (next_states, reward_code u8[B], prob, flags u8[B]), 18 instead of 26 bytes per env over the host link."""
         B = actions.shape[0]
+        if compact:
+            ns, code, prob, flags = out
+            check(lib().mapf_step_host(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
+                                       OPT_COMPACT | (OPT_AUTO_RESET if auto_reset else 0), _ptr(ns), _ptr(code), _ptr(prob),
+                                       _ptr(flags), None))
+            return out
+        ns, reward, prob, done, coll = out
         check(lib().mapf_step_host(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
                                    OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
                                    _ptr(coll)))

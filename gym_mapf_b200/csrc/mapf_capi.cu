@@ -56,6 +56,7 @@ struct DeviceGuard {
 // ---------------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------------
+#define MAPF_HOST_STREAMS 2   // mapf_step_host: the staged path pipelines two halves
 struct mapf_ctx {
     DevSpec sp;
     mapf_info info;
@@ -81,7 +82,7 @@ struct mapf_ctx {
     std::vector<u32> h_cell_rc;
     // mapf_step_host staging
     std::mutex mu;
-    cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaStream_t hs[MAPF_HOST_STREAMS] = {};
     unsigned char *d_stage = nullptr;
     size_t d_stage_bytes = 0;
     unsigned char *h_small = nullptr;   // page-locked scratch of the small-batch host step (mapped into the device)
@@ -161,7 +162,7 @@ extern "C" void mapf_ctx_destroy(mapf_ctx *ctx) {
         cudaFree(ctx->d_colbase);
         cudaFree(ctx->d_stage);
         if (ctx->h_small) cudaFreeHost(ctx->h_small);
-        for (int i = 0; i < 2; ++i)
+        for (int i = 0; i < MAPF_HOST_STREAMS; ++i)
             if (ctx->hs[i]) cudaStreamDestroy(ctx->hs[i]);
     }
     delete ctx;
@@ -543,6 +544,9 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
         {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
         {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
+        {ctx->ks.step_philox1c, ctx->smem_base, &ctx->grid_step1},
+        {ctx->ks.step_philox2c, ctx->smem_base, &ctx->grid_step2},
+        {ctx->ks.step_tape_c, ctx->smem_base, &ctx->grid_step_tape},
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
         {ctx->ks.rollout_philox2, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
@@ -588,6 +592,13 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
 extern "C" int mapf_ctx_info(const mapf_ctx *ctx, mapf_info *out) {
     if (!ctx || !out) return fail(MAPF_ERR_INVALID, "mapf_ctx_info: NULL argument");
     *out = ctx->info;
+    return MAPF_OK;
+}
+
+extern "C" int mapf_ctx_reward_table(const mapf_ctx *ctx, double out64[64]) {
+    if (!ctx || !out64) return fail(MAPF_ERR_INVALID, "mapf_ctx_reward_table: NULL argument");
+    static_assert(4 * MAPF_REW_STRIDE == 64, "reward table layout");
+    memcpy(out64, ctx->pt.reward, 64 * sizeof(double));
     return MAPF_OK;
 }
 
@@ -962,8 +973,9 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         const int32_t *a_actions = actions + off;
         const double *a_u = uniforms ? uniforms + (size_t)off * ctx->sp.n : nullptr;
         void *a_ns = (unsigned char *)next_states + sw * off;
-        double *a_r = reward + off, *a_p = prob + off;
-        uint8_t *a_d = done + off, *a_c = collision + off;
+        const bool compact = (options & MAPF_OPT_COMPACT) != 0;  // reward codes are one byte per env
+        double *a_r = compact ? (double *)((uint8_t *)reward + off) : reward + off, *a_p = prob + off;
+        uint8_t *a_d = done + off, *a_c = collision ? collision + off : nullptr;
         u32 nb = (u32)nb64;
         u64 st = step_index, e0 = (u64)(env_offset + off);
         u32 op = options;
@@ -980,14 +992,14 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         const void *fn;
         int grid;
         if (uniforms) {
-            fn = ctx->ks.step_tape;
+            fn = compact ? ctx->ks.step_tape_c : ctx->ks.step_tape;
             grid = grid_for(nb, ctx->threads, ctx->grid_step_tape);
         } else if (force_ept != 1 && (nb & 1) == 0 && aligned(a_states, 16) && aligned(a_ns, 16) && aligned(a_actions, 8) &&
-                   aligned(a_r, 16) && aligned(a_p, 16) && aligned(a_d, 2) && aligned(a_c, 2)) {
-            fn = ctx->ks.step_philox2;
+                   aligned(a_r, compact ? 2 : 16) && aligned(a_p, 16) && aligned(a_d, 2) && (compact || aligned(a_c, 2))) {
+            fn = compact ? ctx->ks.step_philox2c : ctx->ks.step_philox2;
             grid = grid_for(nb / 2, ctx->threads, ctx->grid_step2);
         } else {
-            fn = ctx->ks.step_philox1;
+            fn = compact ? ctx->ks.step_philox1c : ctx->ks.step_philox1;
             grid = grid_for(nb, ctx->threads, ctx->grid_step1);
         }
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
@@ -1027,7 +1039,8 @@ extern "C" int mapf_step(const mapf_ctx *ctx, const void *states, const int32_t 
                          const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
                          uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
                          uint8_t *collision, void *stream) {
-    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done || !collision)))
+    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done ||
+                                     (!collision && !(options & MAPF_OPT_COMPACT)))))
         return fail(MAPF_ERR_INVALID, "mapf_step: bad argument");
     if (B == 0) return MAPF_OK;
     DeviceGuard g(ctx->device);
@@ -1105,14 +1118,17 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
                               const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
                               uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
                               uint8_t *collision) {
-    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done || !collision)))
+    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done ||
+                                     (!collision && !(options & MAPF_OPT_COMPACT)))))
         return fail(MAPF_ERR_INVALID, "mapf_step_host: bad argument");
+    const bool compact = (options & MAPF_OPT_COMPACT) != 0;
+    const size_t rw = compact ? 1 : 8;  // bytes of a reward / reward code
     if (B == 0) return MAPF_OK;
     std::lock_guard<std::mutex> lock(ctx->mu);
     DeviceGuard g(ctx->device);
     const int n = ctx->sp.n;
     const size_t sw = (size_t)ctx->sp.words * 8;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < MAPF_HOST_STREAMS; ++i)
         if (!ctx->hs[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->hs[i], cudaStreamNonBlocking));
     // Small batches (the scalar MapfEnv.step is B = 1): the fixed cost of eight staged copies dwarfs the work.  Pack
     // the inputs into the context's page-locked scratch, run the kernel directly on its device mapping (zero copy),
@@ -1135,10 +1151,10 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
         memcpy(next_states, h + o_ns, sw * B);
-        memcpy(reward, h + o_r, 8 * (size_t)B);
+        memcpy(reward, h + o_r, rw * (size_t)B);
         memcpy(prob, h + o_p, 8 * (size_t)B);
         memcpy(done, h + o_d, (size_t)B);
-        memcpy(collision, h + o_c, (size_t)B);
+        if (!compact) memcpy(collision, h + o_c, (size_t)B);
         return MAPF_OK;
     }
     // Zero-copy path: when every buffer is page-locked host memory that the device can address (cudaHostAlloc /
@@ -1149,10 +1165,12 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         const void *host_in[3] = {states, actions, uniforms};
         void *host_out[5] = {next_states, reward, prob, done, collision};
         void *dev_in[3] = {nullptr, nullptr, nullptr}, *dev_out[5];
-#ifdef MAPF_TUNING
-        bool mapped = getenv("MAPF_HOST_STAGED") == nullptr;
-#else
+        // (Chunked cudaMemcpyAsync pipelines were measured against this zero-copy launch on 2**20 envs and lost: 8 chunks
+        // over 4 streams 1.29e9 env-steps/s, two halves 1.48e9, zero copy 1.70e9 -- the 7 driver calls per chunk cost
+        // more than the copy engines gain.)
         bool mapped = true;
+#ifdef MAPF_TUNING
+        if (const char *e = getenv("MAPF_HOST_MODE")) mapped = atoi(e) == 0;  // 0 zero-copy, 1 staged copies
 #endif
         for (int i = 0; i < 3 && mapped; ++i) {
             if (!host_in[i]) continue;
@@ -1162,6 +1180,8 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
             dev_in[i] = at.devicePointer;
         }
         for (int i = 0; i < 5 && mapped; ++i) {
+            dev_out[i] = nullptr;
+            if (!host_out[i]) continue;  // collision in compact mode
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, host_out[i]) != cudaSuccess || at.type != cudaMemoryTypeHost ||
                 !at.devicePointer) { cudaGetLastError(); mapped = false; break; }
@@ -1170,9 +1190,15 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
         if (mapped) {
             // one CTA per SM: over PCIe fewer, longer sequential streams move more bytes than a full persistent grid
             // (measured 1.73e9 vs 1.60e9 env-steps/s)
+            // over PCIe fewer, longer sequential streams move more bytes: 2**20 envs with 296 / 148 / 74 / 37 CTAs reach
+            // 1.61 / 1.70 / 1.74 / 1.75e9 env-steps/s (profiles/r02_ablations.txt)
+            int host_grid = B >= (1 << 18) ? (ctx->info.sm_count + 3) / 4 : ctx->info.sm_count;
+#ifdef MAPF_TUNING
+            if (const char *e = getenv("MAPF_HOST_GRID")) host_grid = atoi(e);
+#endif
             int rc = launch_step(ctx, dev_in[0], (const int32_t *)dev_in[1], B, (const double *)dev_in[2], seed, step_index,
                                  env_offset, options, dev_out[0], (double *)dev_out[1], (double *)dev_out[2],
-                                 (uint8_t *)dev_out[3], (uint8_t *)dev_out[4], ctx->hs[0], ctx->info.sm_count);
+                                 (uint8_t *)dev_out[3], (uint8_t *)dev_out[4], ctx->hs[0], host_grid);
             if (rc) return rc;
             CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
             return MAPF_OK;
@@ -1198,10 +1224,13 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
     unsigned char *d_p = p; p += align(8 * (size_t)B);
     unsigned char *d_d = p; p += align((size_t)B);
     unsigned char *d_c = p;
-    const int parts = B >= (1 << 16) ? 2 : 1;
+    // chunk boundaries are even (128-bit I/O)
+    const int parts = B >= (1 << 16) ? 2 : 1;  // pageable buffers: two pipelined halves
     for (int h = 0; h < parts; ++h) {
-        const int64_t b0 = B * h / parts, b1 = B * (h + 1) / parts, nb = b1 - b0;
-        cudaStream_t st = ctx->hs[h];
+        const int64_t b0 = (B * h / parts) & ~(int64_t)1, b1 = h + 1 == parts ? B : ((B * (h + 1) / parts) & ~(int64_t)1),
+                      nb = b1 - b0;
+        if (nb <= 0) continue;
+        cudaStream_t st = ctx->hs[h % MAPF_HOST_STREAMS];
         CUDA_TRY(cudaMemcpyAsync(d_s + sw * b0, (const unsigned char *)states + sw * b0, sw * nb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_a + 4 * b0, (const unsigned char *)actions + 4 * b0, 4 * nb, cudaMemcpyHostToDevice, st));
         if (uniforms)
@@ -1209,16 +1238,16 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
                                      (size_t)n * 8 * nb, cudaMemcpyHostToDevice, st));
         int rc = launch_step(ctx, d_s + sw * b0, (const int32_t *)(d_a + 4 * b0), nb,
                              uniforms ? (const double *)(d_u + (size_t)n * 8 * b0) : nullptr, seed, step_index,
-                             env_offset + b0, options, d_ns + sw * b0, (double *)(d_r + 8 * b0), (double *)(d_p + 8 * b0),
+                             env_offset + b0, options, d_ns + sw * b0, (double *)(d_r + rw * b0), (double *)(d_p + 8 * b0),
                              d_d + b0, d_c + b0, st);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)next_states + sw * b0, d_ns + sw * b0, sw * nb, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync((unsigned char *)reward + 8 * b0, d_r + 8 * b0, 8 * nb, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync((unsigned char *)reward + rw * b0, d_r + rw * b0, rw * nb, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)prob + 8 * b0, d_p + 8 * b0, 8 * nb, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(done + b0, d_d + b0, nb, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(collision + b0, d_c + b0, nb, cudaMemcpyDeviceToHost, st));
+        if (!compact) CUDA_TRY(cudaMemcpyAsync(collision + b0, d_c + b0, nb, cudaMemcpyDeviceToHost, st));
     }
-    for (int h = 0; h < parts; ++h) CUDA_TRY(cudaStreamSynchronize(ctx->hs[h]));
+    for (int h = 0; h < MAPF_HOST_STREAMS; ++h) CUDA_TRY(cudaStreamSynchronize(ctx->hs[h]));
     return MAPF_OK;
 }
 

@@ -7,6 +7,7 @@ struct KernelSet {
     const void *step_philox1 = nullptr;  // k_step<N, W, LUTS, TAPE=false, EPT=1>
     const void *step_philox2 = nullptr;  // ... EPT=2 (128-bit I/O)
     const void *step_tape = nullptr;     // k_step<N, W, LUTS, TAPE=true, EPT=1>
+    const void *step_philox1c = nullptr, *step_philox2c = nullptr, *step_tape_c = nullptr;  // ... COMPACT outputs
     const void *rollout_philox = nullptr, *rollout_tape = nullptr;  // k_rollout<N, W, LUTS, TAPE, EPT=1>
     const void *rollout_philox2 = nullptr;                            // ... EPT=2 (128-bit stores)
     const void *step_lanes_philox = nullptr, *step_lanes_tape = nullptr;  // k_step_lanes<N, TAPE>: 2..8 agents, one-word states

@@ -12,6 +12,9 @@ static void fill(KernelSet *k) {
     k->step_philox1 = (const void *)k_step<N, W, LUTS, false, 1>;
     k->step_philox2 = (const void *)k_step<N, W, LUTS, false, 2>;
     k->step_tape = (const void *)k_step<N, W, LUTS, true, 1>;
+    k->step_philox1c = (const void *)k_step<N, W, LUTS, false, 1, true>;
+    k->step_philox2c = (const void *)k_step<N, W, LUTS, false, 2, true>;
+    k->step_tape_c = (const void *)k_step<N, W, LUTS, true, 1, true>;
     k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false, 1>;
     if constexpr (N <= 6) k->rollout_philox2 = (const void *)k_rollout<N, W, LUTS, false, 2>;
     k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true, 1>;
@@ -25,10 +28,10 @@ static void fill(KernelSet *k) {
     }
     k->expand = (const void *)k_expand<N, W, LUTS, false>;
     k->expand_range = (const void *)k_expand<N, W, LUTS, true>;
-    k->count = (const void *)k_count<N, W, false>;
-    k->count_range = (const void *)k_count<N, W, true>;
-    k->count_partials = (const void *)k_count_partials<N, W, false>;
-    k->count_partials_range = (const void *)k_count_partials<N, W, true>;
+    k->count = (const void *)k_count<N, W, false, LUTS>;
+    k->count_range = (const void *)k_count<N, W, true, LUTS>;
+    k->count_partials = (const void *)k_count_partials<N, W, false, LUTS>;
+    k->count_partials_range = (const void *)k_count_partials<N, W, true, LUTS>;
     k->decode = (const void *)k_decode<N, W>;
     k->encode = (const void *)k_encode<N, W>;
     if (W == 1) {

@@ -207,7 +207,9 @@ __device__ __forceinline__ void row_input(const DevSpec &sp, const u64 *states, 
 }
 
 // len(P[s][a]) (mapf_env.py:448-479): 1 for a terminal state, else the product of merged-outcome counts
-template <int N, int WORDS, bool RANGE>
+// (EXACT: the context guarantees the exact fp64-pipe divisions of the decode, i.e. its move table is staged -- here the
+// table itself is still read through the read-only cache)
+template <int N, int WORDS, bool RANGE, bool EXACT>
 __global__ void __launch_bounds__(256) k_count(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions,
                                                u64 sb_lo, u64 sb_hi, i64 B, i64 *__restrict__ row_len) {
     for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (i64)gridDim.x * blockDim.x) {
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(256) k_count(DevSpec sp, const u64 *__restrict
         u32 a;
         row_input<WORDS, RANGE>(sp, states, actions, sb_lo, sb_hi, b, lo, hi, a);
         int cell[N], act[N];
-        decode_state<N, WORDS>(sp, lo, hi, cell);
+        decode_state<N, WORDS, EXACT>(sp, lo, hi, cell);
         decode_action<N>(a, act);
         i64 len = 1;
         if (!is_terminal<N>(sp, cell, lo, hi)) {
@@ -333,7 +335,7 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
 
 // Row lengths AND the per-chunk sums of the scan in one pass (saves the scan's first read of row_len and a launch):
 // block b owns rows [b * SCAN_CHUNK, (b + 1) * SCAN_CHUNK).
-template <int N, int WORDS, bool RANGE>
+template <int N, int WORDS, bool RANGE, bool EXACT>
 __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *__restrict__ states,
                                                         const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
                                                         i64 *__restrict__ row_len, i64 *__restrict__ partial) {
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
         for (int j = 0; j < 4; ++j) {
             const i64 b = base + (h + j) * 256 + threadIdx.x;
             int cell[N], act[N];
-            decode_state<N, WORDS>(sp, lo[j], hi[j], cell);
+            decode_state<N, WORDS, EXACT>(sp, lo[j], hi[j], cell);
             decode_action<N>(a[j], act);
             i64 len = 1;
             if (!is_terminal<N>(sp, cell, lo[j], hi[j])) {
@@ -1032,6 +1034,7 @@ struct EnvOut {
     u64 lo, hi;
     double reward, prob;
     u32 kind;  // 0 living, 1 clash, 2 goal, 3 step from a terminal state: done = kind != 0, collision = kind == 1
+    u32 rcode; // index of `reward` in the reward table: 16 * kind + parked agents (what MAPF_OPT_COMPACT stores)
 };
 __device__ __forceinline__ u32 out_done(const EnvOut &o) { return o.kind != 0u ? 1u : 0u; }
 __device__ __forceinline__ u32 out_coll(const EnvOut &o) { return o.kind == 1u ? 1u : 0u; }
@@ -1091,8 +1094,8 @@ __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &
     // (s, 0, True, {"prob": 0}) (mapf_env.py:238-240), a no-op that consumes no draw
     const int kind = term ? 3 : (clash ? 1 : (goal ? 2 : 0));
     // living reward: Makespan rows of the table hold the same value for every parked count
-    out.reward = lds_f64<MAPF_SMEM_REW>(
-        tb.base + ((u32)(kind * MAPF_REW_STRIDE) + parked_from_entries<N>(sp, tb.act0, ehi, in.cell, in.actv)) * 8u);
+    out.rcode = (u32)(kind * MAPF_REW_STRIDE) + parked_from_entries<N>(sp, tb.act0, ehi, in.cell, in.actv);
+    out.reward = lds_f64<MAPF_SMEM_REW>(tb.base + out.rcode * 8u);
     out.prob = total;
     out.kind = (u32)kind;
     if (term) {
@@ -1141,7 +1144,9 @@ __device__ __forceinline__ void load_raw(const u64 *states, const int *__restric
 
 // One item (EPT consecutive envs) of k_step: decode, sample, judge, store.  `raw` / `draws` were fetched / generated one
 // iteration ahead by the caller.
-template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
+// COMPACT (MAPF_OPT_COMPACT): `reward` receives one code byte per env instead of the double, `done` the flag byte
+// MAPF_FLAG_DONE | MAPF_FLAG_COLLISION, `coll` nothing: 18 instead of 26 result bytes per env.
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT>
 __device__ __forceinline__ void step_item(const DevSpec &sp, const SmemTables &tb, u32 it,
                                           const RawIn<WORDS, EPT> &raw, const u32 (&draws)[EPT][((N + 3) / 4) * 4],
                                           const double *__restrict__ uniforms, u32 opts, u64 *next_states,
@@ -1176,18 +1181,28 @@ __device__ __forceinline__ void step_item(const DevSpec &sp, const SmemTables &t
             store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
             store_state<WORDS>(next_states, b + 1, o[EPT - 1].lo, o[EPT - 1].hi);
         }
-        reinterpret_cast<double2 *>(reward)[it] = make_double2(o[0].reward, o[EPT - 1].reward);
         reinterpret_cast<double2 *>(prob)[it] = make_double2(o[0].prob, o[EPT - 1].prob);
-        // both flag bytes of both envs from two byte permutes: byte `kind` of 0x01010100 is done, of 0x00000100 collision
         const u32 sel = o[0].kind | (o[EPT - 1].kind << 4);
-        reinterpret_cast<u16 *>(done)[it] = (u16)__byte_perm(0x01010100u, 0u, sel);
-        reinterpret_cast<u16 *>(coll)[it] = (u16)__byte_perm(0x00000100u, 0u, sel);
+        if (COMPACT) {
+            reinterpret_cast<u16 *>(reward)[it] = (u16)(o[0].rcode | (o[EPT - 1].rcode << 8));
+            reinterpret_cast<u16 *>(done)[it] = (u16)__byte_perm(0x01010300u, 0u, sel);  // byte `kind`: done | collision << 1
+        } else {
+            reinterpret_cast<double2 *>(reward)[it] = make_double2(o[0].reward, o[EPT - 1].reward);
+            // both flag bytes of both envs from two byte permutes: byte `kind` of 0x01010100 is done, of 0x00000100 collision
+            reinterpret_cast<u16 *>(done)[it] = (u16)__byte_perm(0x01010100u, 0u, sel);
+            reinterpret_cast<u16 *>(coll)[it] = (u16)__byte_perm(0x00000100u, 0u, sel);
+        }
     } else {
         store_state<WORDS>(next_states, b, o[0].lo, o[0].hi);
-        reward[b] = o[0].reward;
         prob[b] = o[0].prob;
-        done[b] = (u8)out_done(o[0]);
-        coll[b] = (u8)out_coll(o[0]);
+        if (COMPACT) {
+            reinterpret_cast<u8 *>(reward)[b] = (u8)o[0].rcode;
+            done[b] = (u8)(out_done(o[0]) | (out_coll(o[0]) << 1));
+        } else {
+            reward[b] = o[0].reward;
+            done[b] = (u8)out_done(o[0]);
+            coll[b] = (u8)out_coll(o[0]);
+        }
     }
 }
 
@@ -1203,7 +1218,7 @@ __device__ __forceinline__ void item_draws(const PhiloxKeys &keys, u64 env0, u64
     }
 }
 
-template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT = false>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
 k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
        const double *__restrict__ uniforms, u64 step, u64 env0, u32 opts, u64 *next_states,
@@ -1248,7 +1263,8 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         const RawIn<WORDS, EPT> cur = raw;
         const u32 it_next = it + stride;
         if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
-        step_item<N, WORDS, LUTS, TAPE, EPT>(sp, tb, it, cur, draws, uniforms, opts, next_states, reward, prob, done, coll);
+        step_item<N, WORDS, LUTS, TAPE, EPT, COMPACT>(sp, tb, it, cur, draws, uniforms, opts, next_states, reward, prob, done,
+                                                      coll);
 #ifdef MAPF_TRACE
         if (trace_iter == 0) TRACE(4);
         TRACE(8 + trace_iter);

@@ -54,6 +54,11 @@ enum { MAPF_FLAG_DONE = 1, MAPF_FLAG_COLLISION = 2, MAPF_FLAG_TERMINAL = 4 };
 enum {
     MAPF_OPT_AUTO_RESET = 1, /* an env whose step returned done is put back on the start state (next_state holds
                                 the start state for it); off = the reference's semantics (mapf_env.py:237-266) */
+    MAPF_OPT_COMPACT = 4,    /* mapf_step / mapf_step_host: 18 instead of 26 result bytes per env (the host link is the bound
+                                of the end-to-end step).  `reward` then receives ONE BYTE per env, a code into the 64 doubles
+                                of mapf_ctx_reward_table (every reward the env can return, computed in the reference's order:
+                                mapf_env.py:225-235, 436-446), and `done` one byte with MAPF_FLAG_DONE | MAPF_FLAG_COLLISION;
+                                `collision` is not written (may be NULL).  next_states and prob are unchanged. */
     MAPF_OPT_SHARE_SM = 2    /* mapf_step only: launch ONE resident CTA per SM instead of filling the GPU.  For callers
                                 that keep their envs in two independent pools and step each pool on its own stream
                                 (every pool is a chain of dependent launches, mapf_env.py:237-266 called once per env
@@ -153,6 +158,11 @@ int mapf_checksum(const mapf_ctx *ctx, int64_t n_records, int64_t index_base, co
 int mapf_step(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, const double *uniforms,
               uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
               double *reward, double *prob, uint8_t *done, uint8_t *collision, void *stream);
+
+/* The 64 rewards a step can return, indexed by the code MAPF_OPT_COMPACT writes: code = 16 * kind + parked agents, kind
+ * 0 living, 1 clash + living, 2 goal + living, 3 step from a terminal state (0); `parked` counts the agents standing on
+ * their goal that chose STAY under the sum-of-costs criterion (mapf_env.py:441-446; 0 under Makespan). */
+int mapf_ctx_reward_table(const mapf_ctx *ctx, double out64[64]);
 
 /* The same step with the LANE-PER-AGENT mapping (a group of 2/4/8 warp lanes per env, lane i = agent i; vertex
  * conflicts by __match_any_sync, swaps by __shfl_xor_sync, counts by __ballot_sync).  Bit-identical results and the

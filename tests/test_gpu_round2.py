@@ -159,3 +159,66 @@ def test_bench_checker_on_small_cases(torch):
     payload["reward"] = payload["reward"].copy()
     payload["reward"][17] += 1.0
     assert not bench.verify_payload(payload)[0]
+
+
+def test_greedy_bcast_sharded_sweep_three_ranks_one_device(torch):
+    """The fused exchange step of sharded value iteration with THREE ranks' value vectors (all on this device, one
+    stream per rank): every rank's greedy launch stores its shard's new values into every rank's vector, so after the
+    sweep all three vectors equal the single-GPU sweep.  (On a multi-GPU box the pointers are peer mappings; the kernel
+    and the ABI call are the same.)"""
+    from gym_mapf_b200 import sharding
+    env = _env("empty-8-8", 1, 2, soc=False)
+    eng = env.engine
+    nS, nA = int(eng.nS), int(eng.nA)
+    rng = np.random.default_rng(8)
+    V0 = torch.from_numpy(rng.normal(0, 20, nS)).cuda()
+    world = 3
+    shards = [sharding.table_shard(0, nS, world, r) for r in range(world)]
+    assert sum(s.count for s in shards) == nS and shards[0].count != shards[2].count  # uneven shards
+    # reference: one sweep on one "rank"
+    Q_all = eng.backup_range(0, nS, V0, 0.95)
+    V_ref, pi_ref = eng.greedy(Q_all)
+    vectors = [torch.full((nS,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(world)]
+    ptrs = [v.data_ptr() for v in vectors]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    policies = []
+    torch.cuda.synchronize()
+    for r, sh in enumerate(shards):
+        with torch.cuda.stream(streams[r]):
+            Q = eng.backup_range(sh.begin, sh.count, V0, 0.95)
+            policies.append(eng.greedy_bcast(Q, sh.begin, ptrs))
+    torch.cuda.synchronize()
+    for v in vectors:
+        assert torch.equal(v, V_ref)
+    assert torch.equal(torch.cat(policies), pi_ref)
+
+
+def test_compact_result_layout(torch):
+    """MAPF_OPT_COMPACT: reward codes + one flag byte decode to exactly the default results (device buffers, pinned host
+    buffers, pageable host buffers; Philox and replayed-uniform modes; odd batch = scalar kernel, even = 128-bit kernel)."""
+    for name, scen, n, soc in (("room-32-32-4", 1, 4, True), ("room-64-64-8", 1, 8, False)):
+        env = _env(name, scen, n, soc)
+        eng = env.engine
+        table = torch.from_numpy(eng.reward_table()).cuda()
+        for B in (70001, 70000):
+            rng = np.random.default_rng(B)
+            cells = torch.from_numpy(rng.integers(0, min(eng.L, 40), (B, eng.n)).astype(np.int32)).cuda()  # dense: clashes
+            st = eng.encode(cells)
+            st[: B // 3] = eng.states_from_ints([eng.s0] * (B // 3))
+            ac = torch.from_numpy(rng.integers(0, eng.nA, B).astype(np.int32)).cuda()
+            un = torch.from_numpy(rng.random((B, eng.n))).cuda()
+            for uniforms in (None, un):
+                want = eng.step(st, ac, uniforms=uniforms, seed=5, step_index=9, auto_reset=True)
+                ns, code, prob, flags = eng.step(st, ac, uniforms=uniforms, seed=5, step_index=9, auto_reset=True, compact=True)
+                assert torch.equal(ns, want[0]) and torch.equal(prob, want[2])
+                assert torch.equal(table[code.long()].view(torch.int64), want[1].view(torch.int64))
+                assert torch.equal((flags & 1).bool(), want[3]) and torch.equal((flags >> 1).bool(), want[4])
+                assert int(want[4].sum()) > 0 and int(want[3].sum()) > int(want[4].sum())
+            for pinned in (True, False):
+                mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+                out = (mk(torch.empty(eng.state_shape(B), dtype=torch.int64)), mk(torch.empty(B, dtype=torch.uint8)),
+                       mk(torch.empty(B, dtype=torch.float64)), mk(torch.empty(B, dtype=torch.uint8)))
+                eng.step_host(mk(st.cpu()), mk(ac.cpu()), out, seed=5, step_index=9, auto_reset=True, compact=True)
+                ref = eng.step(st, ac, seed=5, step_index=9, auto_reset=True, compact=True)
+                for a, b in zip(out, ref):
+                    assert torch.equal(a, b.cpu()), pinned
