@@ -1188,8 +1188,6 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
             dev_out[i] = at.devicePointer;
         }
         if (mapped) {
-            // one CTA per SM: over PCIe fewer, longer sequential streams move more bytes than a full persistent grid
-            // (measured 1.73e9 vs 1.60e9 env-steps/s)
             // over PCIe fewer, longer sequential streams move more bytes: 2**20 envs with 296 / 148 / 74 / 37 CTAs reach
             // 1.61 / 1.70 / 1.74 / 1.75e9 env-steps/s (profiles/r02_ablations.txt)
             int host_grid = B >= (1 << 18) ? (ctx->info.sm_count + 3) / 4 : ctx->info.sm_count;
