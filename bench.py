@@ -616,6 +616,7 @@ def run_ours(args):
                                                "the algorithmic 12 B/env; 19.4 of the 26 B/env written had reached DRAM "
                                                "when the kernel ended, the rest was still in the 126 MB L2)",
                              "peak_source": peak_src,
+                             "traffic_definition": "per step of 2**20 envs (all pools' launches together), like `achieved`",
                              "kernel": "k_step<4,smem move table>", "bytes_per_unit": STEP_BYTES,
                              "units_per_launch": B // pools, "launches_per_step": pools,
                              "achieved_definition": "38 B x 2**20 envs / (timed region / K steps): the %d launches of a step "
