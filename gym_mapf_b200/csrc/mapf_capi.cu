@@ -353,6 +353,10 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         sg += (u128)goal_id[i] * mul;
         mul *= (u128)L;
     }
+    sp.s0_terminal = s0 == sg ? 1 : 0;  // is_terminal(starts) (mapf_env.py:210-223): every agent on its goal ...
+    for (int i = 0; i < n; ++i)
+        for (int j = i + 1; j < n; ++j)
+            if (start_id[i] == start_id[j]) sp.s0_terminal = 1;  // ... or two agents on one cell
     sp.s0[0] = (u64)s0; sp.s0[1] = (u64)(s0 >> 64);
     sp.sgoal[0] = (u64)sg; sp.sgoal[1] = (u64)(sg >> 64);
 

@@ -67,6 +67,7 @@ struct DevSpec {
     int L;             // free cells
     int words;         // 64-bit words per joint state (1 or 2)
     int soc;           // 1: sum-of-costs living reward (mapf_env.py:440-446)
+    int s0_terminal;   // 1: the start state itself is terminal (two starts on one cell, or every start on its goal)
     int H, Wd;         // grid height / width
     int lut_smem;      // 1: the move table is staged in shared memory
     int cand_mask;     // bit j set: candidate j (intended, right, left) has probability > 0 (mapf_env.py:172)

@@ -1054,11 +1054,14 @@ __device__ __forceinline__ void env_draws(const PhiloxKeys &K, u64 env, u64 step
 // and the same comparison is made on integers: cumsum_j > u  <=>  w <= T_j (the table holds ~T_j).  The host guarantees that the last
 // threshold of every pattern is 2**32 - 1 (the probabilities of a pattern add up to 1), so the index is simply the
 // number of thresholds below w.
+// `non_terminal` (warp-uniform): the caller knows that the state is not terminal -- a rollout with auto-reset after its
+// first step, when the start state is not terminal: a step that was not done leaves distinct cells that are not the
+// goals, a step that was done leaves the start state -- and the duplicate / goal tests are skipped.
 template <int N, int WORDS, bool LUTS, bool TAPE>
 __device__ __forceinline__ EnvOut env_step(const DevSpec &sp, const SmemTables &tb, const EnvIn<N> &in,
-                                           const double *__restrict__ u, u32 opts, int (&nxt)[N]) {
+                                           const double *__restrict__ u, u32 opts, int (&nxt)[N], bool non_terminal = false) {
     double total;
-    const bool term = is_terminal<N>(sp, in.cell, in.lo, in.hi);
+    const bool term = non_terminal ? false : is_terminal<N>(sp, in.cell, in.lo, in.hi);
     u32 ehi[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -1313,10 +1316,12 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 #pragma unroll
         for (int q = 0; q < EPT; ++q) decode_state<N, WORDS, LUTS>(sp, in[q].lo, in[q].hi, in[q].cell);
         if (!ready) { tables_wait<LUTS>(smem); ready = true; }
-        for (i64 t = 0; t < T; ++t) {
+        // with auto-reset every state after the first step is known not to be terminal (see env_step)
+        const bool chain_non_terminal = (opts & 1u) && !sp.s0_terminal;
+        size_t o = b;     // env-major position inside slab t
+        size_t ov = it;   // the same in units of EPT envs
+        for (i64 t = 0; t < T; ++t, o += B, ov += n_items) {
             const u64 stp = step0 + (u64)t;
-            const size_t o = (size_t)t * B + b;   // env-major position inside slab t
-            const size_t ov = (size_t)t * n_items + it;  // the same in units of EPT envs
             u32 a_cur[EPT];
 #pragma unroll
             for (int q = 0; q < EPT; ++q) a_cur[q] = actions ? a_next[q] : random_action(sp, keys, env0 + (u64)(b + q), stp);
@@ -1333,7 +1338,8 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 #pragma unroll
             for (int q = 0; q < EPT; ++q) {
                 load_actions<N>(sp, tb, a_cur[q], in[q].actv);
-                r[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (o + q) * N : nullptr, opts, nxt[q]);
+                r[q] = env_step<N, WORDS, LUTS, TAPE>(sp, tb, in[q], TAPE ? uniforms + (o + q) * N : nullptr, opts, nxt[q],
+                                                      chain_non_terminal && t > 0);
             }
             if (EPT == 2) {
                 if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[ov] = make_ulonglong2(r[0].lo, r[EPT - 1].lo);
