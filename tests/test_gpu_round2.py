@@ -222,3 +222,29 @@ def test_compact_result_layout(torch):
                 ref = eng.step(st, ac, seed=5, step_index=9, auto_reset=True, compact=True)
                 for a, b in zip(out, ref):
                     assert torch.equal(a, b.cpu()), pinned
+
+
+def test_share_sm_and_pools_give_identical_results(torch):
+    """MAPF_OPT_SHARE_SM only changes the launch shape; two pools stepped on two streams reproduce the single launch."""
+    env = _env("room-32-32-4", 1, 4)
+    eng = env.engine
+    B = 1 << 17
+    rng = np.random.default_rng(2)
+    st = eng.encode(torch.from_numpy(rng.integers(0, eng.L, (B, eng.n)).astype(np.int32)).cuda())
+    ac = torch.from_numpy(rng.integers(0, eng.nA, B).astype(np.int32)).cuda()
+    want = eng.step(st, ac, seed=3, step_index=4, env_offset=1000, auto_reset=True)
+    got = eng.step(st, ac, seed=3, step_index=4, env_offset=1000, auto_reset=True, share_sm=True)
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    out = tuple(torch.empty_like(t) for t in want)
+    H = B // 2
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for k, s in enumerate(streams):
+        with torch.cuda.stream(s):
+            sl = slice(k * H, (k + 1) * H)
+            eng.step(st[sl], ac[sl], seed=3, step_index=4, env_offset=1000 + k * H, auto_reset=True, share_sm=True,
+                     out=tuple(t[sl] for t in out))
+    torch.cuda.synchronize()
+    for a, b in zip(want, out):
+        assert torch.equal(a, b)
