@@ -491,6 +491,7 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
     decode_action<N>(a, act);
     const bool term = is_terminal<N>(sp, cell, slo, shi);
     u32 len = 1, twos = 0, threes = 0;
+    if (!term) {  // a terminal row is the single record (1.0, s, 0, True): phase B needs nothing but its state
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
@@ -502,11 +503,11 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
         twos += k == 2u ? 1u : 0u;
         threes += k == 3u ? 1u : 0u;
     }
-    if (term) len = 1;
+    sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
+    }
     sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
     sl.st[0][lane] = slo;
     sl.st[1][lane] = shi;
-    sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
     // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
     // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
     u32 n_pairs = 0;

@@ -405,7 +405,21 @@ def run_all(device_index, world, rank, only=None, quick=False):
     return out
 
 
+def warm_up_clocks(seconds=1.5):
+    """A cold GPU has not ramped its clocks yet: keep the memory system busy for a moment before a standalone measurement
+    (a copy loop, not a GEMM: a dense matmul pushes the board into its power cap and the clocks stay low afterwards).
+    Standalone numbers still read several percent below the same cases inside bench.py, which run after seconds of load."""
+    a = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+    b = torch.empty_like(a)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            b.copy_(a)
+        torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
+    warm_up_clocks()
     only = set(sys.argv[1:]) or None
     for name, entry, _ in run_all(0, 1, 0, only=only):
         print(json.dumps({name: entry}), flush=True)
