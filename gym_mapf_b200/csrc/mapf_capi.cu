@@ -62,6 +62,7 @@ struct mapf_ctx {
     mapf_info info;
     int device = 0;
     int threads = 256;           // CTA size of the hot kernels
+    int threads_expand = 256;    // ... of k_expand (wider for many agents)
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
     size_t smem_backup = 0;      // smem_base + per-warp backup slabs
@@ -542,7 +543,10 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         }
     }
     ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
-    ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.expand_slab_bytes;
+    ctx->threads_expand = ctx->ks.expand_threads ? ctx->ks.expand_threads : ctx->threads;
+    if (ctx->smem_base + (size_t)(ctx->threads_expand / 32) * ctx->ks.expand_slab_bytes > smem_limit)
+        ctx->threads_expand = ctx->threads;  // the wide CTA's slabs do not fit next to this map's table
+    ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads_expand / 32) * ctx->ks.expand_slab_bytes;
     ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
     struct { const void *fn; size_t smem; int *grid; int threads; } plan[] = {
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
@@ -556,8 +560,8 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.step_lanes_philox, ctx->smem_base, &ctx->grid_lanes},
         {ctx->ks.step_lanes_tape, ctx->smem_base, &ctx->grid_lanes_tape},
-        {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand},
-        {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range},
+        {ctx->ks.expand, ctx->smem_expand, &ctx->grid_expand, ctx->threads_expand},
+        {ctx->ks.expand_range, ctx->smem_expand, &ctx->grid_expand_range, ctx->threads_expand},
         {ctx->ks.backup, ctx->smem_backup, &ctx->grid_backup},
         {ctx->ks.backup_range, ctx->smem_backup, &ctx->grid_backup_range}};
     for (auto &pl : plan) {
@@ -781,8 +785,8 @@ static int expand_impl(const mapf_ctx *ctx, bool range, const void *states, cons
     // Work is cut by records (at least 32 per warp); their number is only known on the device, B * 3**n bounds it.
     const double rec_max = (double)B * (double)ctx->info.max_row_len;
     const int64_t lanes = rec_max > 4e18 ? (int64_t)4e18 : (int64_t)rec_max;
-    const int grid = grid_for(lanes, ctx->threads, range ? ctx->grid_expand_range : ctx->grid_expand);
-    LAUNCH(range ? ctx->ks.expand_range : ctx->ks.expand, grid, ctx->threads, ctx->smem_expand, stream, args);
+    const int grid = grid_for(lanes, ctx->threads_expand, range ? ctx->grid_expand_range : ctx->grid_expand);
+    LAUNCH(range ? ctx->ks.expand_range : ctx->ks.expand, grid, ctx->threads_expand, ctx->smem_expand, stream, args);
     return MAPF_OK;
 }
 

@@ -19,6 +19,7 @@ struct KernelSet {
     const void *backup = nullptr, *backup_range = nullptr;  // k_backup<N, LUTS, RANGE>; one-word states only
     const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;
     size_t expand_slab_bytes = 0;        // per warp
+    int expand_threads = 0;              // CTA size of k_expand (0: the context's)
     size_t backup_slab_bytes = 0;        // per warp
 };
 

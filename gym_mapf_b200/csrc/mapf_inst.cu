@@ -42,6 +42,7 @@ static void fill(KernelSet *k) {
     k->pred_emit = (const void *)k_pred_emit<N, W>;
     k->project = (const void *)k_project<N, W>;
     k->expand_slab_bytes = sizeof(ExpandSlab<N>);
+    k->expand_threads = LUTS ? EXPAND_THREADS(N) : 0;  // 0: the context's CTA size
     k->backup_slab_bytes = sizeof(BackupSlab<N>);
 }
 

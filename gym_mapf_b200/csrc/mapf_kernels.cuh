@@ -491,7 +491,8 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
     decode_action<N>(a, act);
     const bool term = is_terminal<N>(sp, cell, slo, shi);
     u32 len = 1, twos = 0, threes = 0;
-    if (!term) {  // a terminal row is the single record (1.0, s, 0, True): phase B needs nothing but its state
+    // (A shortcut that skips this loop for terminal rows was measured: +12 % on all-terminal batches, but the different
+    // register allocation cost 6 and 7 agents 6-9 % -- profiles/r02_ablations.txt.)
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
@@ -503,11 +504,11 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
         twos += k == 2u ? 1u : 0u;
         threes += k == 3u ? 1u : 0u;
     }
-    sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
-    }
+    if (term) len = 1;
     sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
     sl.st[0][lane] = slo;
     sl.st[1][lane] = shi;
+    sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
     // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
     // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
     u32 n_pairs = 0;
@@ -663,8 +664,27 @@ __device__ __forceinline__ RecordOut expand_record_any(const DevSpec &sp, const 
     return expand_record<N, WORDS>(sp, tb, sl, row, flag, o);
 }
 
+// Up to EXPAND_TWO_CTA_MAX_AGENTS agents two 512-thread CTAs fit an SM (staged table + 16 row slabs each) as long as the
+// kernel stays within 64 registers: without the bound a small change in phase A (e.g. the terminal-row shortcut) lets the
+// allocator take 80 and silently halves the occupancy (6 agents: 61 -> 54 % of the roofline).
+// 7 agents compile to 64 registers without a spill under the bound (80 without it: 57.9 -> 63.7 % of the roofline);
+// 8 and 9 agents spill under it and lose 3-6 %.
+#ifndef EXPAND_TWO_CTA_MAX_AGENTS
+#define EXPAND_TWO_CTA_MAX_AGENTS 7
+#endif
+// CTA size of k_expand (with staged tables): from EXPAND_WIDE_MIN_AGENTS agents on only one CTA fits an SM anyway (90-106
+// registers), a 768-thread CTA (80 registers, some spills) brings 24 instead of 16 warps: 8 / 9 agents 51.1 / 47.1 ->
+// 54.0 / 50.1 % of the roofline, 10 agents unchanged.  (The host falls back to 512 threads when the slabs of 24 warps do
+// not fit next to a large staged table.)
+#ifndef EXPAND_WIDE_MIN_AGENTS
+#define EXPAND_WIDE_MIN_AGENTS 8
+#endif
+#ifndef EXPAND_WIDE_THREADS
+#define EXPAND_WIDE_THREADS 768
+#endif
+#define EXPAND_THREADS(N) ((N) >= EXPAND_WIDE_MIN_AGENTS ? EXPAND_WIDE_THREADS : MAPF_MAX_THREADS)
 template <int N, int WORDS, bool LUTS, bool RANGE>
-__global__ void __launch_bounds__(MAPF_MAX_THREADS)
+__global__ void __launch_bounds__(EXPAND_THREADS(N), (N <= EXPAND_TWO_CTA_MAX_AGENTS ? 2 : 1))
 k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
          const i64 *__restrict__ row_ptr, u64 *__restrict__ next_state, double *__restrict__ prob,
          double *__restrict__ reward, u8 *__restrict__ flags) {
