@@ -270,15 +270,27 @@ class MapfEnv(_EnvBase):
         """One sampled joint transition (mapf_env.py:237-266) computed by the step kernel.  The per-agent uniforms
         are drawn here from `self.np_random`, one per agent in agent order and none for a terminal state, so the
         random stream is consumed exactly as the reference consumes it."""
-        eng = self.engine
         buf = self.__dict__.get("_step_buf")
-        if buf is None:  # reused across calls: the scalar path is dominated by fixed costs
-            buf = self._step_buf = dict(
-                state=np.zeros(eng.words, np.uint64), action=np.zeros(1, np.int32),
-                uniforms=np.zeros(self.n_agents, np.float64),
-                out=(np.zeros(eng.words, np.uint64), np.zeros(1, np.float64), np.zeros(1, np.float64),
-                     np.zeros(1, np.uint8), np.zeros(1, np.uint8)))
-        terminal = self.is_terminal(self.state_to_locations(self.s))
+        if buf is None:  # reused across calls: the scalar path is dominated by fixed costs (one launch, one sync)
+            eng = self.engine
+            from .._native import check, lib
+            state, action = np.zeros(eng.words, np.uint64), np.zeros(1, np.int32)
+            uniforms = np.zeros(self.n_agents, np.float64)
+            out = (np.zeros(eng.words, np.uint64), np.zeros(1, np.float64), np.zeros(1, np.float64),
+                   np.zeros(1, np.uint8), np.zeros(1, np.uint8))
+            # the C-ABI call with its arguments marshalled once (the arrays above never move)
+            call = functools.partial(lib().mapf_step_host, eng._h, state.ctypes.data, action.ctypes.data, 1,
+                                     uniforms.ctypes.data, 0, 0, 0, 0, *(o.ctypes.data for o in out))
+            buf = self._step_buf = dict(state=state, action=action, uniforms=uniforms, out=out, call=call, check=check,
+                                        words=eng.words, known=(None, False))
+        # is_terminal(current state): known from the previous step unless the caller moved the env (env.s = ..., reset)
+        # or that step ended in a clash (a swap leaves a non-terminal state, a vertex clash a terminal one)
+        known_s, known_flag = buf["known"]
+        if known_s == self.s:
+            terminal = known_flag
+        else:
+            terminal = self.is_terminal(self.state_to_locations(self.s))
+            buf["known"] = (self.s, terminal)
         uniforms = buf["uniforms"]
         if terminal:
             uniforms[:] = 0.0
@@ -286,17 +298,22 @@ class MapfEnv(_EnvBase):
             uniforms[:] = self.np_random.random_sample(self.n_agents)  # n successive rand() draws, in agent order
         state = buf["state"]
         state[0] = self.s & 0xFFFFFFFFFFFFFFFF
-        if eng.words == 2:
+        if buf["words"] == 2:
             state[1] = self.s >> 64
         buf["action"][0] = a % self.nA
+        rc = buf["call"]()
+        if rc:
+            buf["check"](rc)
         ns, reward, prob, done, coll = buf["out"]
-        eng.step_host(state, buf["action"], buf["out"], uniforms=uniforms)
-        new_state = int(ns[0]) | (int(ns[1]) << 64 if eng.words == 2 else 0)
+        new_state = int(ns[0]) | (int(ns[1]) << 64 if buf["words"] == 2 else 0)
         self.lastaction = a
         if terminal:
             return self.s, 0, True, {"prob": 0}
         self.s = new_state
-        return new_state, float(reward[0]), bool(done[0]), {"prob": float(prob[0]), "collision": bool(coll[0])}
+        is_done, is_coll = bool(done[0]), bool(coll[0])
+        # not done -> distinct cells, not all on their goals; goal reached -> terminal; clash -> decided on the next call
+        buf["known"] = (None, False) if is_coll else (new_state, is_done)
+        return new_state, float(reward[0]), is_done, {"prob": float(prob[0]), "collision": is_coll}
 
     def reset(self):
         self.lastaction = None
