@@ -106,6 +106,7 @@ class MapfEnv(_EnvBase):
     _PREFETCH_RECORDS = 1 << 21
     _PREFETCH_STATES = 64
     _CACHE_STATES = 2048
+    _CACHE_RECORDS = 1 << 23   # records held by the host-side row cache at most
 
     def __init__(self, grid: MapfGrid, n_agents: int, start_locations: tuple, goal_locations: tuple, fail_prob: float,
                  reward_of_collision: float, reward_of_goal: float, reward_of_living: float,
@@ -158,6 +159,7 @@ class MapfEnv(_EnvBase):
         new.__dict__.update(self.__dict__)
         new.P = function_to_get_item_of_object(new._partial_get_transitions)
         new._rows = collections.OrderedDict()
+        new._rows_records = 0
         new.__dict__.pop("_step_buf", None)
         return new
 
@@ -228,16 +230,25 @@ class MapfEnv(_EnvBase):
         if got is None:
             got = producer()
             self._rows[key] = got
-            if len(self._rows) > self._CACHE_STATES:
-                self._rows.popitem(last=False)
+            self._rows_records = getattr(self, "_rows_records", 0) + len(got[2])
+            # bounded by entries AND by records held (a block of C2 rows is ~1e6 records)
+            while len(self._rows) > 1 and (len(self._rows) > self._CACHE_STATES or self._rows_records > self._CACHE_RECORDS):
+                _, old = self._rows.popitem(last=False)
+                self._rows_records -= len(old[2])
         else:
             self._rows.move_to_end(key)
         return got
 
     def _host_csr(self, csr):
+        """Device CSR -> host arrays ready for row slicing: (row_ptr, next states, prob, reward, done, collision)."""
         row_ptr, ns, prob, reward, flags = csr
-        return (row_ptr.cpu().numpy(), self.engine.states_to_ints(ns), prob.cpu().numpy(), reward.cpu().numpy(),
-                flags.cpu().numpy())
+        flags = flags.cpu().numpy()
+        if self.engine.words == 1:
+            ns = ns.cpu().numpy().view(np.uint64)
+        else:
+            ns = np.array(self.engine.states_to_ints(ns), dtype=object)
+        return (row_ptr.cpu().numpy().tolist(), ns, prob.cpu().numpy(), reward.cpu().numpy(), (flags & 1).astype(bool),
+                (flags & 2).astype(bool))
 
     def _get_transitions(self, s, a):
         """P[s][a]: list of ((prob, collision), next_state, reward, done) in itertools.product order
@@ -252,18 +263,20 @@ class MapfEnv(_EnvBase):
             k = max(1, min(self._PREFETCH_STATES, self._PREFETCH_RECORDS // (self.nA * eng.max_row_len)))
             s0 = s - s % k
             n_states = min(k, self.nS - s0)
-            row_ptr, ns, prob, reward, flags = self._fetch(("block", s0), lambda: self._host_csr(eng.table_range(s0, n_states)))
+            row_ptr, ns, prob, reward, done, coll = self._fetch(("block", s0),
+                                                                lambda: self._host_csr(eng.table_range(s0, n_states)))
             row = (s - s0) * self.nA + a
-            lo, hi = int(row_ptr[row]), int(row_ptr[row + 1])
+            lo, hi = row_ptr[row], row_ptr[row + 1]
         else:
             def one_row():
                 import torch
                 acts = torch.tensor([a], dtype=torch.int32, device=eng.torch_device)
                 return self._host_csr(eng.transitions(eng.states_from_ints([s]), acts))
-            row_ptr, ns, prob, reward, flags = self._fetch((s, a), one_row)
-            lo, hi = 0, int(row_ptr[1])
-        return [((float(prob[i]), bool(flags[i] & 2)), ns[i], float(reward[i]), bool(flags[i] & 1))
-                for i in range(lo, hi)]
+            row_ptr, ns, prob, reward, done, coll = self._fetch((s, a), one_row)
+            lo, hi = 0, row_ptr[1]
+        # slices -> Python scalars in C (tolist), then one zip: a few hundred nanoseconds per record
+        return list(zip(zip(prob[lo:hi].tolist(), coll[lo:hi].tolist()), ns[lo:hi].tolist(), reward[lo:hi].tolist(),
+                        done[lo:hi].tolist()))
 
     # ---- sampled step ----------------------------------------------------------------------------------------
     def step(self, a: int):
