@@ -331,9 +331,8 @@ class Engine:
         import torch
         B = states.shape[0]
         self._check_batch(states, actions)
-        row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
         row_ptr, scratch = self._scan_buffers(B)
-        check(lib().mapf_count_scan_rows(self._h, _ptr(states), _ptr(actions), B, _ptr(row_len), _ptr(row_ptr),
+        check(lib().mapf_count_scan_rows(self._h, _ptr(states), _ptr(actions), B, None, _ptr(row_ptr),
                                          _ptr(scratch), self._stream()))
         total = int(row_ptr[-1].item())
         ns, prob, reward, flags = self._alloc_records(total)
@@ -346,9 +345,8 @@ class Engine:
         import torch
         sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
         B = n_states * self.nA
-        row_len = torch.empty(B, dtype=torch.int64, device=self.torch_device)
         row_ptr, scratch = self._scan_buffers(B)
-        check(lib().mapf_count_scan_range(self._h, C.byref(sb), n_states, _ptr(row_len), _ptr(row_ptr), _ptr(scratch),
+        check(lib().mapf_count_scan_range(self._h, C.byref(sb), n_states, None, _ptr(row_ptr), _ptr(scratch),
                                           self._stream()))
         total = int(row_ptr[-1].item())
         ns, prob, reward, flags = self._alloc_records(total)

@@ -704,7 +704,7 @@ extern "C" int mapf_count_range(const mapf_ctx *ctx, const uint64_t s_begin[2], 
 // count + scan in three launches instead of four (see k_count_partials)
 static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, const int32_t *actions, u64 sb_lo, u64 sb_hi,
                            int64_t B, int64_t *row_len, int64_t *row_ptr, void *scratch, void *stream) {
-    if (!row_ptr || (B > 0 && (!row_len || !scratch))) return fail(MAPF_ERR_INVALID, "count_scan: NULL buffer");
+    if (!row_ptr || (B > 0 && !scratch)) return fail(MAPF_ERR_INVALID, "count_scan: NULL buffer");
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (B == 0) {
@@ -715,14 +715,29 @@ static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, 
     if (chunks > 0x7fffffff) return fail(MAPF_ERR_INVALID, "too many rows for one scan");
     DevSpec sp = ctx->sp;
     i64 *partial = (i64 *)scratch;
-    void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
-    LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
-    const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
-    if (chunks <= SCAN_FOLD_MAX_CHUNKS) {  // two launches: every final block adds up the chunk totals before it itself
-        k_scan_final<true><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+    const bool fold = chunks <= SCAN_FOLD_MAX_CHUNKS;  // every final block adds up the chunk totals before it itself
+    if (row_len) {
+        void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
+        LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
+        if (!fold) k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
+        if (fold) k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+        else k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
     } else {
-        k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
-        k_scan_final<false><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+        // the caller does not want the lengths: they live as u16 / u32 behind the chunk totals in the scratch
+        // (mapf_scan_scratch_bytes reserves the room): 8 instead of 16 bytes per row travel between the two passes
+        void *lens = (unsigned char *)scratch + (((size_t)(chunks + 1) * sizeof(i64) + 15) & ~(size_t)15);
+        void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &lens, &partial};
+        LAUNCH(range ? ctx->ks.count_partials_range_c : ctx->ks.count_partials_c, (int)chunks, 256, 0, stream, args);
+        if (!fold) k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        const int vec_ok = ((uintptr_t)row_ptr & 15) == 0 ? 1 : 0;
+        if (ctx->ks.compact_len_bytes == 2) {
+            if (fold) k_scan_final<true, u16><<<(int)chunks, 256, 0, st>>>((const u16 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
+            else k_scan_final<false, u16><<<(int)chunks, 256, 0, st>>>((const u16 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
+        } else {
+            if (fold) k_scan_final<true, u32><<<(int)chunks, 256, 0, st>>>((const u32 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
+            else k_scan_final<false, u32><<<(int)chunks, 256, 0, st>>>((const u32 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
@@ -746,7 +761,8 @@ extern "C" int mapf_count_scan_range(const mapf_ctx *ctx, const uint64_t s_begin
 extern "C" int64_t mapf_scan_scratch_bytes(int64_t B) {
     int64_t chunks = (B + SCAN_CHUNK - 1) / SCAN_CHUNK;
     if (chunks < 1) chunks = 1;
-    return (chunks + 1) * (int64_t)sizeof(int64_t);
+    // chunk totals + (16-byte aligned) room for compact u32 row lengths, used when mapf_count_scan_* gets row_len = NULL
+    return (((chunks + 1) * (int64_t)sizeof(int64_t) + 15) & ~(int64_t)15) + (B < 0 ? 0 : B) * 4 + 16;
 }
 
 extern "C" int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64_t B, int64_t *row_ptr, void *scratch,
@@ -765,10 +781,10 @@ extern "C" int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64
     k_scan_partials<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial);
     const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
     if (chunks <= SCAN_FOLD_MAX_CHUNKS) {
-        k_scan_final<true><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+        k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
     } else {
         k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
-        k_scan_final<false><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+        k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
     }
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;

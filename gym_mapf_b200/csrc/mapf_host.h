@@ -15,6 +15,8 @@ struct KernelSet {
     const void *expand = nullptr, *expand_range = nullptr;
     const void *count = nullptr, *count_range = nullptr;
     const void *count_partials = nullptr, *count_partials_range = nullptr;  // row lengths + the scan's chunk sums
+    const void *count_partials_c = nullptr, *count_partials_range_c = nullptr;  // ... with u16 / u32 lengths
+    int compact_len_bytes = 0;
     const void *decode = nullptr, *encode = nullptr;
     const void *backup = nullptr, *backup_range = nullptr;  // k_backup<N, LUTS, RANGE>; one-word states only
     const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;

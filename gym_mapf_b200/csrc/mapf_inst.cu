@@ -32,6 +32,16 @@ static void fill(KernelSet *k) {
     k->count_range = (const void *)k_count<N, W, true, LUTS>;
     k->count_partials = (const void *)k_count_partials<N, W, false, LUTS>;
     k->count_partials_range = (const void *)k_count_partials<N, W, true, LUTS>;
+    // compact row lengths (kept in the scan's scratch when the caller does not ask for row_len): 3**10 < 2**16
+    if constexpr (N <= 10) {
+        k->count_partials_c = (const void *)k_count_partials<N, W, false, LUTS, u16>;
+        k->count_partials_range_c = (const void *)k_count_partials<N, W, true, LUTS, u16>;
+        k->compact_len_bytes = 2;
+    } else {
+        k->count_partials_c = (const void *)k_count_partials<N, W, false, LUTS, u32>;
+        k->count_partials_range_c = (const void *)k_count_partials<N, W, true, LUTS, u32>;
+        k->compact_len_bytes = 4;
+    }
     k->decode = (const void *)k_decode<N, W>;
     k->encode = (const void *)k_encode<N, W>;
     if (W == 1) {

@@ -291,8 +291,10 @@ static __global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_c
 // in each of four 512-element passes, so every load and store is a fully coalesced 16-byte access (vec_ok: both arrays
 // 16-byte aligned).  FOLD: the chunk's offset is summed here from the raw per-chunk totals (no spine launch); otherwise
 // `partial` has been scanned by k_scan_spine.
-template <bool FOLD>
-static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict__ in, i64 B, const i64 *__restrict__ partial,
+// LEN: type of the row lengths -- i64 (the public row_len arrays), or u16 / u32 for the compact lengths the fused
+// count + scan keeps in its scratch when the caller does not ask for row_len (8 instead of 16 B per row between the passes).
+template <bool FOLD, typename LEN>
+static __global__ void __launch_bounds__(256) k_scan_final(const LEN *__restrict__ in, i64 B, const i64 *__restrict__ partial,
                                                            i64 *__restrict__ row_ptr, int vec_ok) {
     __shared__ i64 ws[8];
     const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
@@ -301,12 +303,18 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
         const i64 i = base + p * 512 + 2 * (i64)threadIdx.x;
-        if (vec_ok && i + 1 < B) {
+        if (sizeof(LEN) == 8 && vec_ok && i + 1 < B) {
             const longlong2 x = *reinterpret_cast<const longlong2 *>(in + i);
             v0[p] = x.x; v1[p] = x.y;
+        } else if (sizeof(LEN) == 2 && i + 1 < B) {  // (the compact array is 4-byte aligned and i is even)
+            const u32 x = *reinterpret_cast<const u32 *>(in + i);
+            v0[p] = (i64)(x & 0xffffu); v1[p] = (i64)(x >> 16);
+        } else if (sizeof(LEN) == 4 && i + 1 < B) {
+            const uint2 x = *reinterpret_cast<const uint2 *>(in + i);
+            v0[p] = (i64)x.x; v1[p] = (i64)x.y;
         } else {
-            v0[p] = i < B ? in[i] : 0;
-            v1[p] = i + 1 < B ? in[i + 1] : 0;
+            v0[p] = i < B ? (i64)in[i] : 0;
+            v1[p] = i + 1 < B ? (i64)in[i + 1] : 0;
         }
     }
     i64 carry;
@@ -335,10 +343,10 @@ static __global__ void __launch_bounds__(256) k_scan_final(const i64 *__restrict
 
 // Row lengths AND the per-chunk sums of the scan in one pass (saves the scan's first read of row_len and a launch):
 // block b owns rows [b * SCAN_CHUNK, (b + 1) * SCAN_CHUNK).
-template <int N, int WORDS, bool RANGE, bool EXACT>
+template <int N, int WORDS, bool RANGE, bool EXACT, typename LEN = i64>
 __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *__restrict__ states,
                                                         const int *__restrict__ actions, u64 sb_lo, u64 sb_hi, i64 B,
-                                                        i64 *__restrict__ row_len, i64 *__restrict__ partial) {
+                                                        LEN *__restrict__ row_len, i64 *__restrict__ partial) {
     __shared__ i64 ws[8];
     const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
     i64 sum = 0;
@@ -365,7 +373,7 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
                 for (int i = 0; i < N; ++i) len *= (i64)ENT_K(__ldg(sp.lut + cell[i] * 5 + act[i]));
             }
             if (b < B) {
-                row_len[b] = len;
+                row_len[b] = (LEN)len;
                 sum += len;
             }
         }

@@ -123,7 +123,9 @@ int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64_t B, int64
                    void *stream);
 
 /* mapf_count_rows + mapf_scan_rows in one call (one launch and one pass over row_len fewer): row_len[B] and
- * row_ptr[B+1] are both written.  The _range form does the same for a table slab. */
+ * row_ptr[B+1] are both written.  row_len may be NULL when only row_ptr is wanted: the lengths then stay in the scratch
+ * as 16- or 32-bit values (8 instead of 16 bytes per row between the two passes).  The _range form does the same for a
+ * table slab. */
 int mapf_count_scan_rows(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, int64_t *row_len,
                          int64_t *row_ptr, void *scratch, void *stream);
 int mapf_count_scan_range(const mapf_ctx *ctx, const uint64_t s_begin[2], int64_t n_states, int64_t *row_len,

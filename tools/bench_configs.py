@@ -111,10 +111,9 @@ def expand_case(tag, env, soc, dev, peak, target_records, seed, window=None, sam
     R = float(rl.double().mean().item())
     B = max(1024, int(target_records / R))
     st, ac = draw(B)
-    row_len = torch.empty(B, dtype=torch.int64, device=dev)
     row_ptr, scratch = eng._scan_buffers(B)
     s = eng._stream()
-    t_count = timed(lambda: check(lib().mapf_count_scan_rows(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_len), _ptr(row_ptr),
+    t_count = timed(lambda: check(lib().mapf_count_scan_rows(eng._h, _ptr(st), _ptr(ac), B, None, _ptr(row_ptr),
                                                              _ptr(scratch), s)))
     total = int(row_ptr[-1].item())
     ns, prob, reward, flags = eng._alloc_records(total)
@@ -154,10 +153,9 @@ def table_slab_case(tag, env, soc, dev, peak, n_states, world, rank):
     s_begin = (eng.s0 + rank * (eng.nS // max(world, 1))) % (eng.nS - n_states)
     sb = (C.c_uint64 * 2)(s_begin & M64, s_begin >> 64)
     B = n_states * nA
-    row_len = torch.empty(B, dtype=torch.int64, device=dev)
     row_ptr, scratch = eng._scan_buffers(B)
     s = eng._stream()
-    t_count = timed(lambda: check(lib().mapf_count_scan_range(eng._h, C.byref(sb), n_states, _ptr(row_len), _ptr(row_ptr),
+    t_count = timed(lambda: check(lib().mapf_count_scan_range(eng._h, C.byref(sb), n_states, None, _ptr(row_ptr),
                                                               _ptr(scratch), s)))
     total = int(row_ptr[-1].item())
     ns, prob, reward, flags = eng._alloc_records(total)
@@ -307,15 +305,14 @@ def c1_case(dev, peak, device_index):
     # the whole table in one batched call
     sb = (C.c_uint64 * 2)(0, 0)
     B = env.nS * env.nA
-    row_len = torch.empty(B, dtype=torch.int64, device=dev)
     row_ptr, scratch = eng._scan_buffers(B)
     st = eng._stream()
-    check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, _ptr(row_len), _ptr(row_ptr), _ptr(scratch), st))
+    check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, None, _ptr(row_ptr), _ptr(scratch), st))
     total = int(row_ptr[-1].item())
     rec = eng._alloc_records(total)
 
     def table():
-        check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, _ptr(row_len), _ptr(row_ptr), _ptr(scratch), st))
+        check(lib().mapf_count_scan_range(eng._h, C.byref(sb), env.nS, None, _ptr(row_ptr), _ptr(scratch), st))
         check(lib().mapf_expand_range(eng._h, C.byref(sb), env.nS, _ptr(row_ptr), _ptr(rec[0]), _ptr(rec[1]), _ptr(rec[2]),
                                       _ptr(rec[3]), st))
     t_b = timed(table, reps=5, warm=2)
