@@ -557,6 +557,9 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         {ctx->ks.step_tape_c, ctx->smem_base, &ctx->grid_step_tape},
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
         {ctx->ks.rollout_philox2, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
+        {ctx->ks.rollout_philox2_rnd, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
+        {ctx->ks.rollout_philox_rnd, ctx->smem_base, &ctx->grid_rollout},
+        {ctx->ks.rollout_tape_rnd, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.rollout_tape, ctx->smem_base, &ctx->grid_rollout_tape},
         {ctx->ks.step_lanes_philox, ctx->smem_base, &ctx->grid_lanes},
         {ctx->ks.step_lanes_tape, ctx->smem_base, &ctx->grid_lanes_tape},
@@ -1120,17 +1123,19 @@ extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32
     u32 op = options, nb = (u32)B;
     void *args[] = {&sp, &keys, &states_inout, &actions, &T, &nb, &uniforms, &st, &e0, &op, &next_states, &reward, &prob,
                     &done, &collision};
+    const bool given = actions != nullptr;
     if (uniforms) {
-        LAUNCH(ctx->ks.rollout_tape, grid_for(B, ctx->threads, ctx->grid_rollout_tape), ctx->threads, ctx->smem_base,
-               stream, args);
-    } else if (ctx->ks.rollout_philox2 && (B & 1) == 0 && aligned(states_inout, 16) && aligned(next_states, 16) && (!actions || aligned(actions, 8)) &&
-               aligned(reward, 16) && aligned(prob, 16) && aligned(done, 2) && aligned(collision, 2)) {
+        LAUNCH(given ? ctx->ks.rollout_tape : ctx->ks.rollout_tape_rnd, grid_for(B, ctx->threads, ctx->grid_rollout_tape),
+               ctx->threads, ctx->smem_base, stream, args);
+    } else if (ctx->ks.rollout_philox2 && (B & 1) == 0 && aligned(states_inout, 16) && aligned(next_states, 16) &&
+               (!actions || aligned(actions, 8)) && aligned(reward, 16) && aligned(prob, 16) && aligned(done, 2) &&
+               aligned(collision, 2)) {
         // two envs per thread, 128-bit stores: every slab t * B of the [T, B] outputs keeps the base alignment (B even)
-        LAUNCH(ctx->ks.rollout_philox2, grid_for(B / 2, MAPF_ROLLOUT2_THREADS, ctx->grid_rollout2), MAPF_ROLLOUT2_THREADS,
-               ctx->smem_base, stream, args);
+        LAUNCH(given ? ctx->ks.rollout_philox2 : ctx->ks.rollout_philox2_rnd,
+               grid_for(B / 2, MAPF_ROLLOUT2_THREADS, ctx->grid_rollout2), MAPF_ROLLOUT2_THREADS, ctx->smem_base, stream, args);
     } else {
-        LAUNCH(ctx->ks.rollout_philox, grid_for(B, ctx->threads, ctx->grid_rollout), ctx->threads, ctx->smem_base, stream,
-               args);
+        LAUNCH(given ? ctx->ks.rollout_philox : ctx->ks.rollout_philox_rnd, grid_for(B, ctx->threads, ctx->grid_rollout),
+               ctx->threads, ctx->smem_base, stream, args);
     }
     return MAPF_OK;
 }

@@ -10,6 +10,7 @@ struct KernelSet {
     const void *step_philox1c = nullptr, *step_philox2c = nullptr, *step_tape_c = nullptr;  // ... COMPACT outputs
     const void *rollout_philox = nullptr, *rollout_tape = nullptr;  // k_rollout<N, W, LUTS, TAPE, EPT=1>
     const void *rollout_philox2 = nullptr;                            // ... EPT=2 (128-bit stores)
+    const void *rollout_philox_rnd = nullptr, *rollout_philox2_rnd = nullptr, *rollout_tape_rnd = nullptr;  // actions == NULL
     const void *step_lanes_philox = nullptr, *step_lanes_tape = nullptr;  // k_step_lanes<N, TAPE>: 2..8 agents, one-word states
     const void *step_group_philox = nullptr, *step_group_tape = nullptr;  // k_step_group<N, W, TAPE>; staged move tables only
     const void *expand = nullptr, *expand_range = nullptr;

@@ -15,9 +15,14 @@ static void fill(KernelSet *k) {
     k->step_philox1c = (const void *)k_step<N, W, LUTS, false, 1, true>;
     k->step_philox2c = (const void *)k_step<N, W, LUTS, false, 2, true>;
     k->step_tape_c = (const void *)k_step<N, W, LUTS, true, 1, true>;
-    k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false, 1>;
-    if constexpr (N <= 6) k->rollout_philox2 = (const void *)k_rollout<N, W, LUTS, false, 2>;
-    k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true, 1>;
+    k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false, 1, true>;
+    k->rollout_philox_rnd = (const void *)k_rollout<N, W, LUTS, false, 1, false>;
+    if constexpr (N <= 6) {
+        k->rollout_philox2 = (const void *)k_rollout<N, W, LUTS, false, 2, true>;
+        k->rollout_philox2_rnd = (const void *)k_rollout<N, W, LUTS, false, 2, false>;
+    }
+    k->rollout_tape = (const void *)k_rollout<N, W, LUTS, true, 1, true>;
+    k->rollout_tape_rnd = (const void *)k_rollout<N, W, LUTS, true, 1, false>;
     if constexpr (LUTS && W == 1 && N >= 2 && N <= 8) {
         k->step_lanes_philox = (const void *)k_step_lanes<N, false>;
         k->step_lanes_tape = (const void *)k_step_lanes<N, true>;

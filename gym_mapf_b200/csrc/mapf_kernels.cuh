@@ -1321,7 +1321,9 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
 #ifndef MAPF_ROLLOUT2_BLOCKS
 #define MAPF_ROLLOUT2_BLOCKS(N) 1
 #endif
-template <int N, int WORDS, bool LUTS, bool TAPE, int EPT>
+// GIVEN: the actions are an input (int32[T, B]); otherwise (actions == NULL) a uniformly random policy is drawn on the
+// device -- two instantiations, so that neither carries the other's registers and code through the step loop.
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool GIVEN>
 __global__ void __launch_bounds__((EPT == 2 ? MAPF_ROLLOUT2_THREADS : MAPF_MAX_THREADS),
                                    (EPT == 2 ? MAPF_ROLLOUT2_BLOCKS(N) : MAPF_MIN_BLOCKS(N)))
 k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ actions, i64 T, u32 B,
@@ -1339,7 +1341,7 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             load_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
-            a_next[q] = actions ? (u32)actions[b + q] : 0u;
+            a_next[q] = GIVEN ? (u32)actions[b + q] : 0u;
             if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step0, in[q]);
         }
 #pragma unroll
@@ -1353,8 +1355,8 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
             const u64 stp = step0 + (u64)t;
             u32 a_cur[EPT];
 #pragma unroll
-            for (int q = 0; q < EPT; ++q) a_cur[q] = actions ? a_next[q] : random_action(sp, keys, env0 + (u64)(b + q), stp);
-            if (actions && t + 1 < T) {  // in flight during the compute below
+            for (int q = 0; q < EPT; ++q) a_cur[q] = GIVEN ? a_next[q] : random_action(sp, keys, env0 + (u64)(b + q), stp);
+            if (GIVEN && t + 1 < T) {  // in flight during the compute below
                 if (EPT == 2) {
                     const int2 a2 = *reinterpret_cast<const int2 *>(actions + o + B);
                     a_next[0] = (u32)a2.x; a_next[EPT - 1] = (u32)a2.y;
