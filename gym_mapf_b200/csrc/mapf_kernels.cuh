@@ -499,8 +499,15 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
     decode_action<N>(a, act);
     const bool term = is_terminal<N>(sp, cell, slo, shi);
     u32 len = 1, twos = 0, threes = 0;
-    // (A shortcut that skips this loop for terminal rows was measured: +12 % on all-terminal batches, but the different
-    // register allocation cost 6 and 7 agents 6-9 % -- profiles/r02_ablations.txt.)
+    // A terminal row is the single record ((1.0, False), s, 0, True) (mapf_env.py:455-456): phase B needs only the state.
+    // (Safe for the register allocation only under k_expand's two-CTA launch bound: without it this early exit took 80
+    // instead of 64 registers at 6 agents -- profiles/r02_ablations.txt.)
+    if (term) {
+        sl.st[0][lane] = slo;
+        sl.st[1][lane] = shi;
+        sl.flag[lane] = 1;
+        return 1u;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         ent[i] = lut_entry<LUTS>(tb, (u32)cell[i], (u32)act[i] * 8u + (LUTS ? tb.lut : 0u));
@@ -512,19 +519,16 @@ __device__ __forceinline__ u32 expand_row_setup(const DevSpec &sp, const SmemTab
         twos += k == 2u ? 1u : 0u;
         threes += k == 3u ? 1u : 0u;
     }
-    if (term) len = 1;
     sl.rcp[lane] = RECIP_POW3[threes] >> twos;  // floor(floor(2**63 / 3**b) / 2**a) = floor(2**63 / (2**a 3**b))
     sl.st[0][lane] = slo;
     sl.st[1][lane] = shi;
     sl.parked[lane] = (u8)parked_agents<N>(sp, cell, act);
     // small agent counts: one bit "some pair can conflict" selects the all-pairs test (cheap for few agents);
     // from EXPAND_LIST_MIN_AGENTS agents on, the conflicting pairs are listed
-    u32 n_pairs = 0;
-    if (!term) {
-        if (N >= EXPAND_LIST_MIN_AGENTS) n_pairs = list_conflict_pairs<N>(cell, ent, sl.pair, lane);
-        else n_pairs = any_pair_can_conflict<N>(cell, ent) ? EXPAND_MAX_PAIRS + 1u : 0u;
-    }
-    sl.flag[lane] = (u8)((term ? 1u : 0u) | (n_pairs <= EXPAND_MAX_PAIRS ? n_pairs << 1 : 16u));
+    u32 n_pairs;
+    if (N >= EXPAND_LIST_MIN_AGENTS) n_pairs = list_conflict_pairs<N>(cell, ent, sl.pair, lane);
+    else n_pairs = any_pair_can_conflict<N>(cell, ent) ? EXPAND_MAX_PAIRS + 1u : 0u;
+    sl.flag[lane] = (u8)(n_pairs <= EXPAND_MAX_PAIRS ? n_pairs << 1 : 16u);
     return len;
 }
 
