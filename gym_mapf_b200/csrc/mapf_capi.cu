@@ -722,7 +722,7 @@ static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, 
     if (row_len) {
         void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
         LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
-        if (!fold) k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        if (!fold) k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
         const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
         if (fold) k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
         else k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
@@ -732,7 +732,7 @@ static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, 
         void *lens = (unsigned char *)scratch + (((size_t)(chunks + 1) * sizeof(i64) + 15) & ~(size_t)15);
         void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &lens, &partial};
         LAUNCH(range ? ctx->ks.count_partials_range_c : ctx->ks.count_partials_c, (int)chunks, 256, 0, stream, args);
-        if (!fold) k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        if (!fold) k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
         const int vec_ok = ((uintptr_t)row_ptr & 15) == 0 ? 1 : 0;
         if (ctx->ks.compact_len_bytes == 2) {
             if (fold) k_scan_final<true, u16><<<(int)chunks, 256, 0, st>>>((const u16 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
@@ -786,7 +786,7 @@ extern "C" int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64
     if (chunks <= SCAN_FOLD_MAX_CHUNKS) {
         k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
     } else {
-        k_scan_spine<<<1, 256, 0, st>>>(partial, chunks);
+        k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
         k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
     }
     CUDA_TRY(cudaGetLastError());

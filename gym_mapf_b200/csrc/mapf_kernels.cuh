@@ -272,17 +272,48 @@ static __global__ void __launch_bounds__(256) k_scan_partials(const i64 *__restr
     if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the per-chunk totals in place; partial[n_chunks] = grand total
-static __global__ void __launch_bounds__(256) k_scan_spine(i64 *partial, i64 n_chunks) {
-    __shared__ i64 ws[8];
+// single block: exclusive scan of the per-chunk totals in place; partial[n_chunks] = grand total.
+// SPINE_THREADS threads, four consecutive totals per thread and pass (4096 per pass): the passes are serial (load ->
+// barriers -> store), so their number is what this launch costs -- 2**26 one-record rows are 32768 chunks = 8 passes
+// (128 passes with 256 threads and one total each took a quarter of the whole count + scan time).
+#define SPINE_THREADS 1024
+static __global__ void __launch_bounds__(SPINE_THREADS) k_scan_spine(i64 *partial, i64 n_chunks) {
+    __shared__ i64 ws[SPINE_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     i64 carry = 0;
-    for (i64 base = 0; base < n_chunks; base += 256) {
-        i64 i = base + threadIdx.x;
-        i64 v = i < n_chunks ? partial[i] : 0;
-        i64 total;
-        i64 ex = block_scan_256(v, ws, total);
-        if (i < n_chunks) partial[i] = carry + ex;
+    for (i64 base = 0; base < n_chunks; base += 4 * SPINE_THREADS) {
+        const i64 i = base + 4 * (i64)threadIdx.x;
+        i64 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i + j < n_chunks ? partial[i + j] : 0;
+        i64 x = (v[0] + v[1]) + (v[2] + v[3]);
+        const i64 mine = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const i64 y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) ws[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            i64 t = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const i64 y = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += y;
+            }
+            ws[lane] = t;
+        }
+        __syncthreads();
+        i64 ex = carry + (x - mine) + (wid > 0 ? ws[wid - 1] : 0);
+        const i64 total = ws[SPINE_THREADS / 32 - 1];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i + j < n_chunks) partial[i + j] = ex;
+            ex += v[j];
+        }
         carry += total;
+        __syncthreads();  // ws is rewritten by the next pass
     }
     if (threadIdx.x == 0) partial[n_chunks] = carry;
 }
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
                                                         LEN *__restrict__ row_len, i64 *__restrict__ partial) {
     __shared__ i64 ws[8];
     const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
-    i64 sum = 0;
+    u32 sum = 0;  // eight rows of at most 3**13 records
     // two halves of four rows: the four rows' inputs are loaded before the first is decoded (memory-level parallelism)
 #pragma unroll
     for (int h = 0; h < SCAN_CHUNK / 256; h += 4) {
@@ -367,10 +398,11 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
             int cell[N], act[N];
             decode_state<N, WORDS, EXACT>(sp, lo[j], hi[j], cell);
             decode_action<N>(a[j], act);
-            i64 len = 1;
+            u32 len = 1;
             if (!is_terminal<N>(sp, cell, lo[j], hi[j])) {
+                const u32 *hi_words = reinterpret_cast<const u32 *>(sp.lut) + 1;  // k sits in the entry's high word
 #pragma unroll
-                for (int i = 0; i < N; ++i) len *= (i64)ENT_K(__ldg(sp.lut + cell[i] * 5 + act[i]));
+                for (int i = 0; i < N; ++i) len *= (__ldg(hi_words + 2u * ((u32)cell[i] * 5u + (u32)act[i])) >> 24) & 3u;
             }
             if (b < B) {
                 row_len[b] = (LEN)len;
@@ -379,7 +411,7 @@ __global__ void __launch_bounds__(256) k_count_partials(DevSpec sp, const u64 *_
         }
     }
     i64 total;
-    block_scan_256(sum, ws, total);
+    block_scan_256((i64)sum, ws, total);
     if (threadIdx.x == 0) partial[blockIdx.x] = total;
 }
 

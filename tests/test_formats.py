@@ -351,7 +351,8 @@ def test_lane_mapping_unsupported():
 
 # ---- exclusive scan of row lengths (mapf_scan_rows): folded and spine paths, aligned and unaligned buffers ------------
 @gpu
-@pytest.mark.parametrize("B", [1, 2, 511, 512, 513, 2047, 2048, 2049, 100001, (2048 * 2048) + 4097])
+@pytest.mark.parametrize("B", [1, 2, 511, 512, 513, 2047, 2048, 2049, 100001, (2048 * 2048) + 4097,
+                               2 * 4096 * 2048 + 12345])   # the last one: three passes of the spine kernel
 def test_scan_rows_matches_cumsum(B):
     import torch
     from engine_util import make_engine
