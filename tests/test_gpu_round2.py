@@ -248,3 +248,41 @@ def test_share_sm_and_pools_give_identical_results(torch):
     torch.cuda.synchronize()
     for a, b in zip(want, out):
         assert torch.equal(a, b)
+
+
+def test_count_scan_without_row_len_at_chunk_boundaries(torch):
+    """row_ptr from the fused count + scan called with row_len = NULL (compact lengths in the scratch) equals the cumulative
+    sum of mapf_count_rows at sizes around the chunk edges, for one- and two-word states, batch and slab mode, and with an
+    only 8-byte aligned row_ptr."""
+    import ctypes as C
+    from gym_mapf_b200._native import _ptr, check, lib
+    sizes = (1, 2, 511, 2047, 2048, 2049, 8191, 8192, 8193, 3 * 8192 + 77, 1_000_003)
+    for name, scen, n, soc in (("empty-32-32", 1, 2, True), ("room-32-32-4", 1, 4, True), ("room-64-64-8", 1, 8, False)):
+        env = _env(name, scen, n, soc)
+        eng = env.engine
+        for B in sizes:
+            rng = np.random.default_rng(B + n)
+            cells = torch.from_numpy(rng.integers(0, min(eng.L, 200), (B, eng.n)).astype(np.int32)).cuda()
+            st = eng.encode(cells)
+            ac = torch.from_numpy(rng.integers(0, eng.nA, B).astype(np.int32)).cuda()
+            row_len = torch.empty(B, dtype=torch.int64, device="cuda")
+            check(lib().mapf_count_rows(eng._h, _ptr(st), _ptr(ac), B, _ptr(row_len), eng._stream()))
+            want = torch.zeros(B + 1, dtype=torch.int64, device="cuda")
+            want[1:] = torch.cumsum(row_len, 0)
+            for shift in (0, 1):
+                buf = torch.full((B + 4,), -7, dtype=torch.int64, device="cuda")
+                row_ptr = buf[shift:shift + B + 1]
+                scratch = torch.empty(int(lib().mapf_scan_scratch_bytes(B)) // 8 + 1, dtype=torch.int64, device="cuda")
+                check(lib().mapf_count_scan_rows(eng._h, _ptr(st), _ptr(ac), B, None, _ptr(row_ptr), _ptr(scratch),
+                                                 eng._stream()))
+                assert torch.equal(row_ptr, want), (name, B, shift)
+                assert int(buf[shift + B + 1]) == -7 and (shift == 0 or int(buf[0]) == -7)
+        # slab mode: n_states x nA rows
+        n_states = max(1, 20000 // eng.nA + 1)
+        s_begin = eng.s0
+        B = n_states * eng.nA
+        sb = (C.c_uint64 * 2)(s_begin & ((1 << 64) - 1), s_begin >> 64)
+        row_len = torch.empty(B, dtype=torch.int64, device="cuda")
+        check(lib().mapf_count_range(eng._h, C.byref(sb), n_states, _ptr(row_len), eng._stream()))
+        row_ptr = eng.table_range(s_begin, n_states)[0]
+        assert torch.equal(row_ptr[1:], torch.cumsum(row_len, 0)) and int(row_ptr[0]) == 0
