@@ -704,6 +704,22 @@ extern "C" int mapf_count_range(const mapf_ctx *ctx, const uint64_t s_begin[2], 
     return count_impl(ctx, true, nullptr, nullptr, s_begin[0], s_begin[1], B, row_len, stream);
 }
 
+// Launch behind the previous kernel of the stream with programmatic stream serialization: the grid may be scheduled while
+// the predecessor drains (the kernel itself waits, grid_dependency_wait(), before it reads the predecessor's output).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int threads, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // count + scan in three launches instead of four (see k_count_partials)
 static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, const int32_t *actions, u64 sb_lo, u64 sb_hi,
                            int64_t B, int64_t *row_len, int64_t *row_ptr, void *scratch, void *stream) {
@@ -719,28 +735,28 @@ static int count_scan_impl(const mapf_ctx *ctx, bool range, const void *states, 
     DevSpec sp = ctx->sp;
     i64 *partial = (i64 *)scratch;
     const bool fold = chunks <= SCAN_FOLD_MAX_CHUNKS;  // every final block adds up the chunk totals before it itself
+    const int nc = (int)chunks;
     if (row_len) {
         void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &row_len, &partial};
-        LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, (int)chunks, 256, 0, stream, args);
-        if (!fold) k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
+        LAUNCH(range ? ctx->ks.count_partials_range : ctx->ks.count_partials, nc, 256, 0, stream, args);
+        if (!fold) CUDA_TRY(launch_dependent(k_scan_spine, 1, SPINE_THREADS, st, partial, chunks));
         const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
-        if (fold) k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
-        else k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
+        CUDA_TRY(launch_dependent(fold ? k_scan_final<true, i64> : k_scan_final<false, i64>, nc, 256, st, (const i64 *)row_len,
+                                  B, (const i64 *)partial, (i64 *)row_ptr, vec_ok));
     } else {
         // the caller does not want the lengths: they live as u16 / u32 behind the chunk totals in the scratch
         // (mapf_scan_scratch_bytes reserves the room): 8 instead of 16 bytes per row travel between the two passes
         void *lens = (unsigned char *)scratch + (((size_t)(chunks + 1) * sizeof(i64) + 15) & ~(size_t)15);
         void *args[] = {&sp, &states, &actions, &sb_lo, &sb_hi, &B, &lens, &partial};
-        LAUNCH(range ? ctx->ks.count_partials_range_c : ctx->ks.count_partials_c, (int)chunks, 256, 0, stream, args);
-        if (!fold) k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
+        LAUNCH(range ? ctx->ks.count_partials_range_c : ctx->ks.count_partials_c, nc, 256, 0, stream, args);
+        if (!fold) CUDA_TRY(launch_dependent(k_scan_spine, 1, SPINE_THREADS, st, partial, chunks));
         const int vec_ok = ((uintptr_t)row_ptr & 15) == 0 ? 1 : 0;
-        if (ctx->ks.compact_len_bytes == 2) {
-            if (fold) k_scan_final<true, u16><<<(int)chunks, 256, 0, st>>>((const u16 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
-            else k_scan_final<false, u16><<<(int)chunks, 256, 0, st>>>((const u16 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
-        } else {
-            if (fold) k_scan_final<true, u32><<<(int)chunks, 256, 0, st>>>((const u32 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
-            else k_scan_final<false, u32><<<(int)chunks, 256, 0, st>>>((const u32 *)lens, B, partial, (i64 *)row_ptr, vec_ok);
-        }
+        if (ctx->ks.compact_len_bytes == 2)
+            CUDA_TRY(launch_dependent(fold ? k_scan_final<true, u16> : k_scan_final<false, u16>, nc, 256, st, (const u16 *)lens, B,
+                                      (const i64 *)partial, (i64 *)row_ptr, vec_ok));
+        else
+            CUDA_TRY(launch_dependent(fold ? k_scan_final<true, u32> : k_scan_final<false, u32>, nc, 256, st, (const u32 *)lens, B,
+                                      (const i64 *)partial, (i64 *)row_ptr, vec_ok));
     }
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
@@ -783,12 +799,10 @@ extern "C" int mapf_scan_rows(const mapf_ctx *ctx, const int64_t *row_len, int64
     i64 *partial = (i64 *)scratch;
     k_scan_partials<<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial);
     const int vec_ok = (((uintptr_t)row_len | (uintptr_t)row_ptr) & 15) == 0 ? 1 : 0;
-    if (chunks <= SCAN_FOLD_MAX_CHUNKS) {
-        k_scan_final<true, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
-    } else {
-        k_scan_spine<<<1, SPINE_THREADS, 0, st>>>(partial, chunks);
-        k_scan_final<false, i64><<<(int)chunks, 256, 0, st>>>((const i64 *)row_len, B, partial, (i64 *)row_ptr, vec_ok);
-    }
+    const bool fold = chunks <= SCAN_FOLD_MAX_CHUNKS;
+    if (!fold) CUDA_TRY(launch_dependent(k_scan_spine, 1, SPINE_THREADS, st, partial, chunks));
+    CUDA_TRY(launch_dependent(fold ? k_scan_final<true, i64> : k_scan_final<false, i64>, (int)chunks, 256, st,
+                              (const i64 *)row_len, B, (const i64 *)partial, (i64 *)row_ptr, vec_ok));
     CUDA_TRY(cudaGetLastError());
     return MAPF_OK;
 }

@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(256) k_count(DevSpec sp, const u64 *__restrict
 // Exclusive scan of row lengths (three small kernels; chunk = 2048 elements per block)
 // =====================================================================================================
 #define SCAN_CHUNK 2048
+// A kernel launched with programmatic stream serialization may start before its predecessor in the stream has finished;
+// everything after this wait sees the predecessor's writes.  (A no-op for an ordinary launch.)
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ i64 block_scan_256(i64 v, i64 *warp_sums, i64 &block_total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     i64 x = v;
@@ -281,6 +284,7 @@ static __global__ void __launch_bounds__(SPINE_THREADS) k_scan_spine(i64 *partia
     __shared__ i64 ws[SPINE_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     i64 carry = 0;
+    grid_dependency_wait();  // launched with programmatic stream serialization behind the kernel that writes `partial`
     for (i64 base = 0; base < n_chunks; base += 4 * SPINE_THREADS) {
         const i64 i = base + 4 * (i64)threadIdx.x;
         i64 v[4];
@@ -331,6 +335,7 @@ static __global__ void __launch_bounds__(256) k_scan_final(const LEN *__restrict
     const i64 base = (i64)blockIdx.x * SCAN_CHUNK;
     constexpr int PASSES = SCAN_CHUNK / 512;
     i64 v0[PASSES], v1[PASSES];
+    grid_dependency_wait();  // launched with programmatic stream serialization behind the producer of `in` / `partial`
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
         const i64 i = base + p * 512 + 2 * (i64)threadIdx.x;
