@@ -583,15 +583,40 @@ def run_ours(args):
         e2e["compact"] = {"value": world * B * n_e2e / dtc, "unit": "transitions/s", "h2d_bytes_per_step": B * 12 * world,
                           "d2h_bytes_per_step": B * 18 * world, "host_link_gbs": world * B * 30 * n_e2e / dtc / 1e9,
                           "api": "mapf_step_host with MAPF_OPT_COMPACT (reward = reward_table[code], flags = done | collision << 1)"}
+        # The memcpy ceiling of THIS box for the same traffic, measured live: every rank copies the step's 12 B/env in and
+        # 26 B/env out between the same pinned buffers and device memory with cudaMemcpyAsync on two streams at once
+        # (what tools/pcie_peak.py does; boxes of the pool differ by 1.5x in host fabric, so a committed figure misleads).
+        d_in = (torch.empty_like(hs, device=dev), torch.empty_like(ha, device=dev))
+        d_out = tuple(torch.empty_like(t, device=dev) for t in hout)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copy_mix(n):
+            for _ in range(n):
+                with torch.cuda.stream(s_in):
+                    d_in[0].copy_(hs, non_blocking=True)
+                    d_in[1].copy_(ha, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    for h, d in zip(hout, d_out):
+                        h.copy_(d, non_blocking=True)
+            torch.cuda.synchronize()
+
+        copy_mix(3)
+        barrier()
+        t0 = time.perf_counter()
+        copy_mix(n_e2e)
+        dtm = max_ranks(time.perf_counter() - t0)
+        mix_gbs = world * B * 38 * n_e2e / dtm / 1e9
+        e2e["pcie_ceiling"] = {"step_mix_total_gbs": mix_gbs, "env_steps_per_s": world * B * n_e2e / dtm,
+                               "source": "measured live on this box: cudaMemcpyAsync of the step's buffers (12 B/env H2D, 26 B/env "
+                                         "D2H, pinned memory, two streams, %d GPU(s) at the same time)" % world}
+        e2e["pcie_frac"] = e2e["host_link_gbs"] / mix_gbs
         ceil_path = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
-        if os.path.exists(ceil_path):  # measured PCIe ceilings of this pool's boxes (tools/pcie_peak.py), if committed
+        if os.path.exists(ceil_path):  # the same mix measured with tools/pcie_peak.py on another box of the pool
             with open(ceil_path) as f:
                 ceil = json.load(f).get(str(world))
             if ceil:
-                e2e["pcie_ceiling"] = {"step_mix_total_gbs": ceil["step_mix_total_gbs"], "both_total_gbs": ceil["both_total_gbs"],
-                                       "source": "profiles/r02_pcie_ceiling.json (tools/pcie_peak.py: %d GPUs copying "
-                                                 "concurrently, pinned memory, 12 : 26 byte in / out mix)" % world}
-                e2e["pcie_frac"] = e2e["host_link_gbs"] / ceil["step_mix_total_gbs"]
+                e2e["pcie_ceiling"]["committed_other_box_gbs"] = ceil["step_mix_total_gbs"]
+        del d_in, d_out
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)
 
