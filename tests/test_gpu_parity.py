@@ -1,5 +1,7 @@
 """GPU parity: the CUDA path (through the C ABI, include/mapf_b200.h) against the reference-generated golden
 fixtures and against the C oracle on seeded inputs.  Integer fields and fp64 bit patterns must be identical."""
+import os
+
 import numpy as np
 import pytest
 
@@ -587,7 +589,7 @@ def test_fuzz_random_specs(torch):
     """Differential test on 80 random env specs (tiny grids down to a single free cell, 1-5 agents, every noise level
     including 0 and 1, both criteria, starts/goals that may coincide): rows, steps with given uniforms, the fused
     backup, predecessors and projections must equal the C oracle bit for bit."""
-    rng = np.random.default_rng(2026)
+    rng = np.random.default_rng(int(os.environ.get("MAPF_FUZZ_SEED", "2026")))
     for case in range(80):
         spec = _random_spec(rng)
         eng = make_engine(spec)
@@ -629,6 +631,54 @@ def test_fuzz_random_specs(torch):
         # the device-side sampling mode needs slip probabilities that add up to 1 (always true here)
         eng.step(st, at, seed=case)
         eng.close()
+
+
+def test_fuzz_medium_agent_counts(torch):
+    """Differential test for 6-9 agents on random 8..16 x 8..16 grids (one- and two-word states; the conflict pair lists
+    from 8 agents on, the head cache from 9): agents drawn from a small window so that vertex and swap conflicts are
+    frequent; rows of up to a few thousand records and steps with given uniforms against the C oracle."""
+    rng = np.random.default_rng(int(os.environ.get("MAPF_FUZZ_SEED", "91")))
+    words_seen = set()
+    for case in range(16):
+        n = 6 + case % 4
+        lo_side, hi_side = (13, 17) if n == 9 else (8, 13)   # 9 agents on >= 128 free cells need two words
+        H, W = int(rng.integers(lo_side, hi_side)), int(rng.integers(lo_side, hi_side))
+        grid = rng.random((H, W)) < 0.12
+        free = [(r, c) for r in range(H) for c in range(W) if not grid[r, c]]
+        pick = lambda: [list(free[int(rng.integers(0, len(free)))]) for _ in range(n)]  # noqa: E731
+        spec = dict(rows=["".join("@" if v else "." for v in row) for row in grid], n_agents=n, starts=pick(), goals=pick(),
+                    fail_prob=float(rng.choice([0.2, 0.5, 1.0])), r_clash=-1000.0, r_goal=100.0, r_living=-1.0,
+                    soc=bool(rng.integers(0, 2)))
+        eng = make_engine(spec)
+        ora = make_oracle(spec)
+        words_seen.add(eng.words)
+        B = 2000
+        window = min(eng.L, 3 * n)
+        cells = rng.integers(0, window, (B, n)).astype(np.int32)
+        cells[::2] = np.stack([rng.permutation(window)[:n] for _ in range(len(cells[::2]))])  # no duplicates: not terminal
+        lo, hi = ora.encode(cells)
+        st = states_tensor(eng, lo, hi)
+        a = rng.integers(0, eng.nA, B).astype(np.int64)
+        at = torch.from_numpy(a.astype(np.int32)).to(eng.torch_device)
+        uni = rng.random((B, n))
+        ws = ora.step(lo, hi, a, uni)
+        ns, reward, prob, done, coll = eng.step(st, at, uniforms=torch.from_numpy(uni).to(eng.torch_device))
+        glo, ghi = split_states(eng, ns)
+        assert np.array_equal(glo, ws["next_lo"]) and np.array_equal(ghi, ws["next_hi"]), (case, eng.L, n)
+        assert np.array_equal(u64(prob), G.f64_to_bits(ws["prob"])) and np.array_equal(u64(reward), G.f64_to_bits(ws["reward"]))
+        assert np.array_equal(coll.cpu().numpy().astype(np.uint8), ws["collision"])
+        assert int(ws["collision"].sum()) > 0
+        # rows: about half of the agents move, so a row has up to 3**(n/2) records
+        m = 40
+        digits = (rng.random((m, n)) < 0.5) * rng.integers(1, 5, (m, n))
+        ar = (digits * (5 ** np.arange(n))).sum(axis=1).astype(np.int64)
+        want = ora.rows(lo[:m], hi[:m], ar)
+        got = eng.transitions(st[:m], torch.from_numpy(ar.astype(np.int32)).to(eng.torch_device))
+        assert_rows_equal(eng, got, want["row_ptr"], want["next_lo"], want["next_hi"], G.f64_to_bits(want["prob"]),
+                          G.f64_to_bits(want["reward"]), want["done"], want["collision"])
+        assert int(want["collision"].sum()) > 0, (case, n)
+        eng.close()
+    assert words_seen == {1, 2}
 
 
 def test_fuzz_two_word_specs(torch):
