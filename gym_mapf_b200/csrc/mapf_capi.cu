@@ -79,6 +79,9 @@ struct mapf_ctx {
     unsigned char *d_image = nullptr;   // DevSpec::image; the move table is its tail
     u64 *d_lut = nullptr;               // = d_image + (MAPF_SMEM_LUT - MAPF_SMEM_IMG)
     u32 *d_cell_rc = nullptr, *d_colbits = nullptr, *d_colbase = nullptr;
+#ifdef MAPF_BITMAP_ENTRIES
+    unsigned char *d_image_bm = nullptr;  // experiment build: pattern tables + the obstacle bitmap blob
+#endif
     std::vector<u64> h_lut;
     std::vector<u32> h_cell_rc;
     // mapf_step_host staging
@@ -160,6 +163,9 @@ extern "C" void mapf_ctx_destroy(mapf_ctx *ctx) {
         cudaFree(ctx->d_image);
         cudaFree(ctx->d_cell_rc);
         cudaFree(ctx->d_colbits);
+#ifdef MAPF_BITMAP_ENTRIES
+        cudaFree(ctx->d_image_bm);
+#endif
         cudaFree(ctx->d_colbase);
         cudaFree(ctx->d_stage);
         if (ctx->h_small) cudaFreeHost(ctx->h_small);
@@ -471,6 +477,9 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
 
     // ---- launch geometry: stage the move table in shared memory when it leaves room for the per-warp scratch
     const size_t smem_limit = (size_t)prop.sharedMemPerBlockOptin;
+#ifdef MAPF_BITMAP_ENTRIES
+    size_t bm_blob = 0;
+#endif
     KernelSet probe;
     if (!pick_kernels(n, sp.words, true, &probe)) {
         mapf_ctx_destroy(ctx);
@@ -519,6 +528,46 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         CTX_TRY(cudaMemcpy(ctx->d_image, head.data(), image_head, cudaMemcpyHostToDevice));
         sp.image = ctx->d_image;
         sp.image_bytes = (u32)(image_head + (luts ? lut_pad : 0));
+#ifdef MAPF_BITMAP_ENTRIES
+        // Experiment build (make variant EXTRA=-DMAPF_BITMAP_ENTRIES; tools/bitmap_entries_check.py): when the move table is
+        // not staged, stage the obstacle bitmap instead (words, word ranks, cell positions) and derive the entries on the
+        // fly (bm_lut_entry).  Bit-exact, measured 3.2x slower than the L2 gathers in the step: not shipped.
+        if (!luts && sp.cand_mask == 7 && H <= 256 && W <= 256) {
+            const size_t nw = (size_t)W * wpc;
+            const size_t off_rank = nw * 4, off_pos = (off_rank + nw * 2 + 3) & ~(size_t)3;
+            bm_blob = (off_pos + (size_t)L * 2 + 15) & ~(size_t)15;
+            std::vector<unsigned char> blob(bm_blob, 0);
+            memcpy(blob.data(), colbits.data(), nw * 4);
+            uint16_t *wr = reinterpret_cast<uint16_t *>(blob.data() + off_rank);
+            for (int c = 0; c < W; ++c) {
+                u32 acc = colbase[c];
+                for (int w = 0; w < wpc; ++w) { wr[(size_t)c * wpc + w] = (uint16_t)acc; acc += (u32)__builtin_popcount(colbits[(size_t)c * wpc + w]); }
+            }
+            uint16_t *ps = reinterpret_cast<uint16_t *>(blob.data() + off_pos);
+            for (int id = 0; id < L; ++id) ps[id] = (uint16_t)((ctx->h_cell_rc[id] >> 16) | ((ctx->h_cell_rc[id] & 0xffffu) << 8));
+            CTX_TRY(cudaMalloc(&ctx->d_image_bm, image_head + bm_blob));
+            CTX_TRY(cudaMemcpy(ctx->d_image_bm, head.data(), image_head, cudaMemcpyHostToDevice));
+            CTX_TRY(cudaMemcpy(ctx->d_image_bm + image_head, blob.data(), bm_blob, cudaMemcpyHostToDevice));
+            sp.image = ctx->d_image_bm;
+            sp.image_bytes = (u32)(image_head + bm_blob);
+            sp.bm_wrank_off = (u32)off_rank;
+            sp.bm_pos_off = (u32)off_pos;
+            sp.bm_wpc = (u32)wpc;
+            auto pat_of = [&](u32 triple) {
+                for (int p = 0; p < ctx->n_patterns; ++p)
+                    if (ctx->pat_triple[p] == triple) return (u32)(p * MAPF_PAT_STRIDE);
+                return 0u;
+            };
+            const u32 none = pat_of(1u | (2u << 3) | (4u << 6)) | (3u << 8);
+            sp.bm_pat[0] = sp.bm_pat[1] = sp.bm_pat[2] = sp.bm_pat[4] = (u16)none;
+            sp.bm_pat[3] = (u16)(pat_of(3u | (4u << 3)) | (2u << 8));
+            sp.bm_pat[5] = (u16)(pat_of(5u | (2u << 3)) | (2u << 8));
+            sp.bm_pat[6] = (u16)(pat_of(1u | (6u << 3)) | (2u << 8));
+            sp.bm_pat[7] = (u16)(pat_of(7u) | (1u << 8));
+            sp.bm_pat_stay = (pat_of(7u) << 16) | (1u << 24);
+            ctx->threads = 512;
+        }
+#endif
     }
     pick_kernels(n, sp.words, luts, &ctx->ks);
     memset(&ctx->lanes, 0, sizeof(ctx->lanes));
@@ -543,6 +592,9 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         }
     }
     ctx->smem_base = MAPF_SMEM_LUT + (luts ? lut_pad : 0);  // barrier + image
+#ifdef MAPF_BITMAP_ENTRIES
+    ctx->smem_base += bm_blob;
+#endif
     ctx->threads_expand = ctx->ks.expand_threads ? ctx->ks.expand_threads : ctx->threads;
     if (ctx->smem_base + (size_t)(ctx->threads_expand / 32) * ctx->ks.expand_slab_bytes > smem_limit)
         ctx->threads_expand = ctx->threads;  // the wide CTA's slabs do not fit next to this map's table

@@ -746,7 +746,7 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 lane_le = 0xffffffffu >> (31 - lane);
-    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
+    ExpandSlab<N> &sl = reinterpret_cast<ExpandSlab<N> *>(smem + MAPF_SMEM_LUT + staged_table_bytes<LUTS>(sp))[wid];
     const i64 M = row_ptr[B];
     const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
     // Records are dealt out in chunks of consecutive records, chunk c to warp c mod n_warps, EXPAND_CHUNKS_PER_WARP(N)
@@ -859,7 +859,7 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     const u32 FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u32 lane_le = 0xffffffffu >> (31 - lane);
-    BackupSlab<N> &bs = reinterpret_cast<BackupSlab<N> *>(smem + MAPF_SMEM_LUT + (LUTS ? sp.lut_bytes : 0))[wid];
+    BackupSlab<N> &bs = reinterpret_cast<BackupSlab<N> *>(smem + MAPF_SMEM_LUT + staged_table_bytes<LUTS>(sp))[wid];
     ExpandSlab<N> &sl = bs.sl;
     const i64 n_batches = (B + 31) >> 5;
     const i64 n_warps = (i64)gridDim.x * (blockDim.x >> 5);
