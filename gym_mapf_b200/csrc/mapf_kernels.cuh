@@ -783,6 +783,18 @@ k_expand(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
             // ---------------- phase A: rows r .. r + 31 (those that start before `hi`)
             const i64 b = r + lane;
             const i64 start = b < B ? row_ptr[b] : M;
+#ifndef EXPAND_PREFETCH_ROWS
+#define EXPAND_PREFETCH_ROWS 32
+#endif
+            if (EXPAND_PREFETCH_ROWS > 0 && b + EXPAND_PREFETCH_ROWS < B) {
+                // the next batch's row starts and inputs: on their way to L2 while this batch is expanded (short rows are
+                // bound by the two dependent round trips per batch: 2 agents 59.8 -> 63.2 % of the roofline)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr + b + EXPAND_PREFETCH_ROWS));
+                if (!RANGE) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(states + (b + EXPAND_PREFETCH_ROWS) * WORDS));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + b + EXPAND_PREFETCH_ROWS));
+                }
+            }
             const i64 batch_begin = __shfl_sync(FULL, start, 0);
             const bool need = b < B && start < hi;
             const u32 len = need ? expand_row_setup<N, WORDS, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, sb_hi, b) : 0u;
@@ -867,6 +879,10 @@ k_backup(DevSpec sp, const u64 *__restrict__ states, const int *__restrict__ act
     for (i64 batch = (i64)blockIdx.x * (blockDim.x >> 5) + wid; batch < n_batches; batch += n_warps) {
         const i64 b = batch * 32 + lane;
         const bool need = b < B;
+        if (!RANGE && b + 32 * n_warps < B) {  // this warp's next batch of inputs (see k_expand)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(states + b + 32 * n_warps));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(actions + b + 32 * n_warps));
+        }
         HeadCache hc;
         hc.row = -1;
         const u32 len = need ? expand_row_setup<N, 1, LUTS, RANGE>(sp, tb, sl, lane, states, actions, sb_lo, 0ull, b) : 0u;
