@@ -1402,7 +1402,8 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 #pragma unroll
         for (int q = 0; q < EPT; ++q) {
             load_state<WORDS>(states, b + q, in[q].lo, in[q].hi);
-            a_next[q] = GIVEN ? (u32)actions[b + q] : 0u;
+            // the random policy's action is drawn one step ahead as well (its Philox block is off the step's critical path)
+            a_next[q] = GIVEN ? (u32)actions[b + q] : random_action(sp, keys, env0 + (u64)(b + q), step0);
             if (!TAPE) env_draws<N>(keys, env0 + (u64)(b + q), step0, in[q]);
         }
 #pragma unroll
@@ -1416,7 +1417,7 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
             const u64 stp = step0 + (u64)t;
             u32 a_cur[EPT];
 #pragma unroll
-            for (int q = 0; q < EPT; ++q) a_cur[q] = GIVEN ? a_next[q] : random_action(sp, keys, env0 + (u64)(b + q), stp);
+            for (int q = 0; q < EPT; ++q) a_cur[q] = a_next[q];
             if (GIVEN && t + 1 < T) {  // in flight during the compute below
                 if (EPT == 2) {
                     const int2 a2 = *reinterpret_cast<const int2 *>(actions + o + B);
@@ -1459,6 +1460,7 @@ k_rollout(DevSpec sp, PhiloxKeys keys, u64 *states, const int *__restrict__ acti
 #pragma unroll
                 for (int i = 0; i < N; ++i) in[q].cell[i] = nxt[q][i];
                 if (!TAPE && t + 1 < T) env_draws<N>(keys, env0 + (u64)(b + q), stp + 1, in[q]);
+                if (!GIVEN && t + 1 < T) a_next[q] = random_action(sp, keys, env0 + (u64)(b + q), stp + 1);
             }
         }
 #pragma unroll
