@@ -557,33 +557,45 @@ def run_ours(args):
                 torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.float64).pin_memory(),
                 torch.empty(B, dtype=torch.bool).pin_memory(), torch.empty(B, dtype=torch.bool).pin_memory())
         n_e2e = max(3, min(K, 30))
-        for i in range(3):
-            eng.step_host(hs, ha, hout, seed=seed, step_index=i, env_offset=env_offset, auto_reset=True)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            eng.step_host(hs, ha, hout, seed=seed, step_index=10 + i, env_offset=env_offset, auto_reset=True)
-        torch.cuda.synchronize()
-        dt = max_ranks(time.perf_counter() - t0)
+
+        def host_leg(call):
+            for i in range(3):
+                call(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_e2e):
+                call(10 + i)
+            torch.cuda.synchronize()
+            return max_ranks(time.perf_counter() - t0)
+
+        # Headline: the batched MapfEnv.step(action) -- like the reference's env object (self.s, mapf_env.py:237, 264) the
+        # engine keeps the envs' states, on the device; every step the host sends the actions (4 B/env) and receives
+        # next_state, reward, done, prob and collision (26 B/env) in pinned host memory.
+        ds = states[0].clone()
+        dt = host_leg(lambda i: eng.step_host_resident(ds, ha, hout, seed=seed, step_index=i, env_offset=env_offset,
+                                                       auto_reset=True))
         e2e = {"value": world * B * n_e2e / dt, "unit": "transitions/s",
-               "h2d_bytes_per_step": B * 12 * world, "d2h_bytes_per_step": B * 26 * world, "steps": n_e2e,
-               "api": "mapf_step_host (C ABI, pinned host buffers in and out)",
+               "h2d_bytes_per_step": B * 4 * world, "d2h_bytes_per_step": B * 26 * world, "steps": n_e2e,
+               "api": "mapf_step_host_resident (C ABI: states resident on the device as in the reference's env object, "
+                      "actions from and all five results to pinned host buffers)",
                "host_numa_bind": prev_affinity is not None,
-               "host_link_gbs": world * B * 38 * n_e2e / dt / 1e9}
+               "host_link_gbs": world * B * 30 * n_e2e / dt / 1e9}
+        if rank == 0:  # the resident states ARE the returned next states
+            assert torch.equal(ds.cpu(), hout[0]), "mapf_step_host_resident: device states differ from the returned ones"
+        # the stateless call (round-1 headline): the states cross the link too, 12 B/env in
+        dts = host_leg(lambda i: eng.step_host(hs, ha, hout, seed=seed, step_index=i, env_offset=env_offset, auto_reset=True))
+        e2e["stateless"] = {"value": world * B * n_e2e / dts, "unit": "transitions/s", "h2d_bytes_per_step": B * 12 * world,
+                            "d2h_bytes_per_step": B * 26 * world, "host_link_gbs": world * B * 38 * n_e2e / dts / 1e9,
+                            "api": "mapf_step_host (states and actions from pinned host buffers)"}
         # opt-in compact result layout (MAPF_OPT_COMPACT: reward code + one flag byte, 18 instead of 26 B/env back)
         cout = (hout[0], torch.empty(B, dtype=torch.uint8).pin_memory(), hout[2], torch.empty(B, dtype=torch.uint8).pin_memory())
-        for i in range(3):
-            eng.step_host(hs, ha, cout, seed=seed, step_index=i, env_offset=env_offset, auto_reset=True, compact=True)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            eng.step_host(hs, ha, cout, seed=seed, step_index=10 + i, env_offset=env_offset, auto_reset=True, compact=True)
-        torch.cuda.synchronize()
-        dtc = max_ranks(time.perf_counter() - t0)
-        e2e["compact"] = {"value": world * B * n_e2e / dtc, "unit": "transitions/s", "h2d_bytes_per_step": B * 12 * world,
-                          "d2h_bytes_per_step": B * 18 * world, "host_link_gbs": world * B * 30 * n_e2e / dtc / 1e9,
-                          "api": "mapf_step_host with MAPF_OPT_COMPACT (reward = reward_table[code], flags = done | collision << 1)"}
-        # The memcpy ceiling of THIS box for the same traffic, measured live: every rank copies the step's 12 B/env in and
+        dtc = host_leg(lambda i: eng.step_host_resident(ds, ha, cout, seed=seed, step_index=i, env_offset=env_offset,
+                                                        auto_reset=True, compact=True))
+        e2e["compact"] = {"value": world * B * n_e2e / dtc, "unit": "transitions/s", "h2d_bytes_per_step": B * 4 * world,
+                          "d2h_bytes_per_step": B * 18 * world, "host_link_gbs": world * B * 22 * n_e2e / dtc / 1e9,
+                          "api": "mapf_step_host_resident with MAPF_OPT_COMPACT (reward = reward_table[code], flags = done | "
+                                 "collision << 1)"}
+        # The memcpy ceiling of THIS box for the same traffic, measured live: every rank copies the step's 4 B/env in and
         # 26 B/env out between the same pinned buffers and device memory with cudaMemcpyAsync on two streams at once
         # (what tools/pcie_peak.py does; boxes of the pool differ by 1.5x in host fabric, so a committed figure misleads).
         d_in = (torch.empty_like(hs, device=dev), torch.empty_like(ha, device=dev))
@@ -593,7 +605,6 @@ def run_ours(args):
         def copy_mix(n):
             for _ in range(n):
                 with torch.cuda.stream(s_in):
-                    d_in[0].copy_(hs, non_blocking=True)
                     d_in[1].copy_(ha, non_blocking=True)
                 with torch.cuda.stream(s_out):
                     for h, d in zip(hout, d_out):
@@ -605,17 +616,11 @@ def run_ours(args):
         t0 = time.perf_counter()
         copy_mix(n_e2e)
         dtm = max_ranks(time.perf_counter() - t0)
-        mix_gbs = world * B * 38 * n_e2e / dtm / 1e9
+        mix_gbs = world * B * 30 * n_e2e / dtm / 1e9
         e2e["pcie_ceiling"] = {"step_mix_total_gbs": mix_gbs, "env_steps_per_s": world * B * n_e2e / dtm,
-                               "source": "measured live on this box: cudaMemcpyAsync of the step's buffers (12 B/env H2D, 26 B/env "
+                               "source": "measured live on this box: cudaMemcpyAsync of the step's buffers (4 B/env H2D, 26 B/env "
                                          "D2H, pinned memory, two streams, %d GPU(s) at the same time)" % world}
         e2e["pcie_frac"] = e2e["host_link_gbs"] / mix_gbs
-        ceil_path = os.path.join(ROOT, "profiles", "r02_pcie_ceiling.json")
-        if os.path.exists(ceil_path):  # the same mix measured with tools/pcie_peak.py on another box of the pool
-            with open(ceil_path) as f:
-                ceil = json.load(f).get(str(world))
-            if ceil:
-                e2e["pcie_ceiling"]["committed_other_box_gbs"] = ceil["step_mix_total_gbs"]
         del d_in, d_out
         if prev_affinity is not None:
             os.sched_setaffinity(0, prev_affinity)

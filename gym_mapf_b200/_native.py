@@ -21,7 +21,7 @@ FLAG_DONE, FLAG_COLLISION = 1, 2
 EXPORTS = ["mapf_ctx_create", "mapf_ctx_destroy", "mapf_ctx_info", "mapf_ctx_moves", "mapf_ctx_reward_table", "mapf_decode_states",
            "mapf_encode_states", "mapf_count_rows", "mapf_scan_scratch_bytes", "mapf_scan_rows", "mapf_count_scan_rows",
            "mapf_count_scan_range", "mapf_expand",
-           "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_step_lanes", "mapf_rollout", "mapf_step_host",
+           "mapf_count_range", "mapf_expand_range", "mapf_checksum", "mapf_step", "mapf_step_lanes", "mapf_rollout", "mapf_step_host", "mapf_step_host_resident",
            "mapf_backup", "mapf_backup_range", "mapf_greedy", "mapf_greedy_bcast", "mapf_count_predecessors", "mapf_predecessors",
            "mapf_projected_words", "mapf_project_states", "mapf_parse_map_text", "mapf_parse_scen_text", "mapf_ctx_create_from_text", "mapf_ctx_grid",
            "mapf_group_create", "mapf_group_destroy", "mapf_group_size", "mapf_group_step", "mapf_last_error",
@@ -96,6 +96,7 @@ def lib():
         L.mapf_step_lanes.argtypes = L.mapf_step.argtypes
         L.mapf_rollout.argtypes = [vp, vp, vp, i64, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp, vp]
         L.mapf_step_host.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp]
+        L.mapf_step_host_resident.argtypes = [vp, vp, vp, i64, vp, u64, u64, i64, u32, vp, vp, vp, vp, vp]
         L.mapf_backup.argtypes = [vp, vp, vp, i64, vp, i64, C.c_double, vp, vp]
         L.mapf_backup_range.argtypes = [vp, C.POINTER(u64 * 2), i64, vp, i64, C.c_double, vp, vp]
         L.mapf_greedy.argtypes = [vp, vp, i64, vp, vp, vp]
@@ -445,6 +446,26 @@ class Engine:
         check(lib().mapf_step_host(self._h, _ptr(states), _ptr(actions), B, _ptr(uniforms), seed, step_index, env_offset,
                                    OPT_AUTO_RESET if auto_reset else 0, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done),
                                    _ptr(coll)))
+        return out
+
+    def step_host_resident(self, states_dev, actions, out, uniforms=None, seed=0, step_index=0, env_offset=0,
+                           auto_reset=False, compact=False):
+        """`step_host` for envs whose states stay on the device (the reference's env keeps `self.s`; `step` receives
+        only the action): `states_dev` (device tensor) is advanced in place, only `actions` crosses the host link on
+        the way in.  `out` as for `step_host`; results are bit-identical to it."""
+        import torch
+        B = actions.shape[0]
+        self._check_tensor("states_dev", states_dev, torch.int64, self.state_shape(B))
+        torch.cuda.current_stream(self.device_index).synchronize()  # the call runs on the context's own streams
+        opts = (OPT_COMPACT if compact else 0) | (OPT_AUTO_RESET if auto_reset else 0)
+        if compact:
+            ns, code, prob, flags = out
+            check(lib().mapf_step_host_resident(self._h, _ptr(states_dev), _ptr(actions), B, _ptr(uniforms), seed, step_index,
+                                                env_offset, opts, _ptr(ns), _ptr(code), _ptr(prob), _ptr(flags), None))
+            return out
+        ns, reward, prob, done, coll = out
+        check(lib().mapf_step_host_resident(self._h, _ptr(states_dev), _ptr(actions), B, _ptr(uniforms), seed, step_index,
+                                            env_offset, opts, _ptr(ns), _ptr(reward), _ptr(prob), _ptr(done), _ptr(coll)))
         return out
 
     # ---- rows next to the hot path (SURVEY.md 8f) ----------------------------------------------------------

@@ -600,7 +600,14 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
         ctx->threads_expand = ctx->threads;  // the wide CTA's slabs do not fit next to this map's table
     ctx->smem_expand = ctx->smem_base + (size_t)(ctx->threads_expand / 32) * ctx->ks.expand_slab_bytes;
     ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
+    int grid_keep = 0;  // the KEEP kernels are launched with their plain twins' grids (host-link-bound callers)
     struct { const void *fn; size_t smem; int *grid; int threads; } plan[] = {
+        {ctx->ks.step_philox1k, ctx->smem_base, &grid_keep},
+        {ctx->ks.step_philox2k, ctx->smem_base, &grid_keep},
+        {ctx->ks.step_tape_k, ctx->smem_base, &grid_keep},
+        {ctx->ks.step_philox1ck, ctx->smem_base, &grid_keep},
+        {ctx->ks.step_philox2ck, ctx->smem_base, &grid_keep},
+        {ctx->ks.step_tape_ck, ctx->smem_base, &grid_keep},
         {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
         {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
         {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
@@ -1045,7 +1052,7 @@ static PhiloxKeys make_keys(uint64_t seed) {
 static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B, const double *uniforms,
                        uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
                        double *reward, double *prob, uint8_t *done, uint8_t *collision, cudaStream_t stream,
-                       int grid_limit = 0) {
+                       int grid_limit = 0, void *keep = nullptr) {
     if (!uniforms && !ctx->philox_ok)
         return fail(MAPF_ERR_UNSUPPORTED, "device-side sampling needs slip probabilities that add up to 1; pass uniforms");
     const size_t sw = (size_t)ctx->sp.words * 8;
@@ -1069,6 +1076,7 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         const bool compact = (options & MAPF_OPT_COMPACT) != 0;  // reward codes are one byte per env
         double *a_r = compact ? (double *)((uint8_t *)reward + off) : reward + off, *a_p = prob + off;
         uint8_t *a_d = done + off, *a_c = collision ? collision + off : nullptr;
+        void *a_keep = keep ? (unsigned char *)keep + sw * off : nullptr;  // KEEP kernels: second copy of the next states
         u32 nb = (u32)nb64;
         u64 st = step_index, e0 = (u64)(env_offset + off);
         u32 op = options;
@@ -1078,21 +1086,23 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             if (const char *e = getenv("MAPF_TRACE_PTR")) trace_buf = (const double *)strtoull(e, nullptr, 0);
         }
         void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, uniforms ? (void *)&a_u : (void *)&trace_buf, &st, &e0, &op,
-                        &a_ns, &a_r, &a_p, &a_d, &a_c};
+                        &a_ns, &a_r, &a_p, &a_d, &a_c, &a_keep};
 #else
-        void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, &a_u, &st, &e0, &op, &a_ns, &a_r, &a_p, &a_d, &a_c};
+        void *args[] = {&sp, &keys, &a_states, &a_actions, &nb, &a_u, &st, &e0, &op, &a_ns, &a_r, &a_p, &a_d, &a_c, &a_keep};
 #endif
         const void *fn;
         int grid;
+        const KernelSet &ks = ctx->ks;
         if (uniforms) {
-            fn = compact ? ctx->ks.step_tape_c : ctx->ks.step_tape;
+            fn = keep ? (compact ? ks.step_tape_ck : ks.step_tape_k) : (compact ? ks.step_tape_c : ks.step_tape);
             grid = grid_for(nb, ctx->threads, ctx->grid_step_tape);
         } else if (force_ept != 1 && (nb & 1) == 0 && aligned(a_states, 16) && aligned(a_ns, 16) && aligned(a_actions, 8) &&
-                   aligned(a_r, compact ? 2 : 16) && aligned(a_p, 16) && aligned(a_d, 2) && (compact || aligned(a_c, 2))) {
-            fn = compact ? ctx->ks.step_philox2c : ctx->ks.step_philox2;
+                   aligned(a_r, compact ? 2 : 16) && aligned(a_p, 16) && aligned(a_d, 2) && (compact || aligned(a_c, 2)) &&
+                   aligned(a_keep, 16)) {
+            fn = keep ? (compact ? ks.step_philox2ck : ks.step_philox2k) : (compact ? ks.step_philox2c : ks.step_philox2);
             grid = grid_for(nb / 2, ctx->threads, ctx->grid_step2);
         } else {
-            fn = compact ? ctx->ks.step_philox1c : ctx->ks.step_philox1;
+            fn = keep ? (compact ? ks.step_philox1ck : ks.step_philox1k) : (compact ? ks.step_philox1c : ks.step_philox1);
             grid = grid_for(nb, ctx->threads, ctx->grid_step1);
         }
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
@@ -1209,13 +1219,22 @@ extern "C" int mapf_rollout(const mapf_ctx *ctx, void *states_inout, const int32
 // ---------------------------------------------------------------------------------------------------------------
 // host-buffer step: H2D, step, D2H in two pipelined halves on the context's own streams
 // ---------------------------------------------------------------------------------------------------------------
-extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B,
-                              const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
-                              uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
-                              uint8_t *collision) {
-    if (!ctx || B < 0 || (B > 0 && (!states || !actions || !next_states || !reward || !prob || !done ||
+// `keep` != NULL (mapf_step_host_resident): the envs' states live in DEVICE memory at `keep`; they are read from there
+// instead of from the host pointer `states` (ignored) and overwritten in place with the next states by the KEEP kernels.
+static int step_host_impl(mapf_ctx *ctx, const void *states, void *keep, const int32_t *actions, int64_t B,
+                          const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
+                          uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
+                          uint8_t *collision) {
+    if (!ctx || B < 0 || (B > 0 && ((!states && !keep) || !actions || !next_states || !reward || !prob || !done ||
                                      (!collision && !(options & MAPF_OPT_COMPACT)))))
-        return fail(MAPF_ERR_INVALID, "mapf_step_host: bad argument");
+        return fail(MAPF_ERR_INVALID, "%s: bad argument", keep ? "mapf_step_host_resident" : "mapf_step_host");
+    if (keep && B > 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, keep) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != ctx->device) {
+            cudaGetLastError();
+            return fail(MAPF_ERR_INVALID, "mapf_step_host_resident: states_dev must be device memory of the context's GPU");
+        }
+    }
     const bool compact = (options & MAPF_OPT_COMPACT) != 0;
     const size_t rw = compact ? 1 : 8;  // bytes of a reward / reward code
     if (B == 0) return MAPF_OK;
@@ -1237,12 +1256,12 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
             CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->h_small_dev, ctx->h_small, 0));
         }
         unsigned char *h = ctx->h_small, *d = ctx->h_small_dev;
-        memcpy(h + o_s, states, sw * B);
+        if (!keep) memcpy(h + o_s, states, sw * B);
         memcpy(h + o_a, actions, 4 * (size_t)B);
         if (uniforms) memcpy(h + o_u, uniforms, (size_t)n * 8 * B);
-        int rc = launch_step(ctx, d + o_s, (const int32_t *)(d + o_a), B, uniforms ? (const double *)(d + o_u) : nullptr, seed,
-                             step_index, env_offset, options, d + o_ns, (double *)(d + o_r), (double *)(d + o_p), d + o_d,
-                             d + o_c, ctx->hs[0]);
+        int rc = launch_step(ctx, keep ? keep : d + o_s, (const int32_t *)(d + o_a), B,
+                             uniforms ? (const double *)(d + o_u) : nullptr, seed, step_index, env_offset, options, d + o_ns,
+                             (double *)(d + o_r), (double *)(d + o_p), d + o_d, d + o_c, ctx->hs[0], 0, keep);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
         memcpy(next_states, h + o_ns, sw * B);
@@ -1267,7 +1286,7 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
 #ifdef MAPF_TUNING
         if (const char *e = getenv("MAPF_HOST_MODE")) mapped = atoi(e) == 0;  // 0 zero-copy, 1 staged copies
 #endif
-        for (int i = 0; i < 3 && mapped; ++i) {
+        for (int i = keep ? 1 : 0; i < 3 && mapped; ++i) {
             if (!host_in[i]) continue;
             cudaPointerAttributes at;
             if (cudaPointerGetAttributes(&at, host_in[i]) != cudaSuccess || at.type != cudaMemoryTypeHost ||
@@ -1289,15 +1308,16 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
 #ifdef MAPF_TUNING
             if (const char *e = getenv("MAPF_HOST_GRID")) host_grid = atoi(e);
 #endif
-            int rc = launch_step(ctx, dev_in[0], (const int32_t *)dev_in[1], B, (const double *)dev_in[2], seed, step_index,
-                                 env_offset, options, dev_out[0], (double *)dev_out[1], (double *)dev_out[2],
-                                 (uint8_t *)dev_out[3], (uint8_t *)dev_out[4], ctx->hs[0], host_grid);
+            int rc = launch_step(ctx, keep ? keep : dev_in[0], (const int32_t *)dev_in[1], B, (const double *)dev_in[2], seed,
+                                 step_index, env_offset, options, dev_out[0], (double *)dev_out[1], (double *)dev_out[2],
+                                 (uint8_t *)dev_out[3], (uint8_t *)dev_out[4], ctx->hs[0], host_grid, keep);
             if (rc) return rc;
             CUDA_TRY(cudaStreamSynchronize(ctx->hs[0]));
             return MAPF_OK;
         }
     }
     // per-env device bytes: state in, action, uniforms, state out, reward, prob, done, collision
+    // (resident states: the kernels of the two halves work on disjoint env ranges of `keep`, in place)
     const size_t per_env = sw + 4 + (uniforms ? (size_t)n * 8 : 0) + sw + 8 + 8 + 1 + 1;
     const size_t need = per_env * (size_t)B + 8 * 256;
     if (need > ctx->d_stage_bytes) {
@@ -1324,15 +1344,17 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
                       nb = b1 - b0;
         if (nb <= 0) continue;
         cudaStream_t st = ctx->hs[h % MAPF_HOST_STREAMS];
-        CUDA_TRY(cudaMemcpyAsync(d_s + sw * b0, (const unsigned char *)states + sw * b0, sw * nb, cudaMemcpyHostToDevice, st));
+        if (!keep)
+            CUDA_TRY(cudaMemcpyAsync(d_s + sw * b0, (const unsigned char *)states + sw * b0, sw * nb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(d_a + 4 * b0, (const unsigned char *)actions + 4 * b0, 4 * nb, cudaMemcpyHostToDevice, st));
         if (uniforms)
             CUDA_TRY(cudaMemcpyAsync(d_u + (size_t)n * 8 * b0, (const unsigned char *)uniforms + (size_t)n * 8 * b0,
                                      (size_t)n * 8 * nb, cudaMemcpyHostToDevice, st));
-        int rc = launch_step(ctx, d_s + sw * b0, (const int32_t *)(d_a + 4 * b0), nb,
+        unsigned char *k0 = keep ? (unsigned char *)keep + sw * b0 : nullptr;
+        int rc = launch_step(ctx, keep ? k0 : d_s + sw * b0, (const int32_t *)(d_a + 4 * b0), nb,
                              uniforms ? (const double *)(d_u + (size_t)n * 8 * b0) : nullptr, seed, step_index,
                              env_offset + b0, options, d_ns + sw * b0, (double *)(d_r + rw * b0), (double *)(d_p + 8 * b0),
-                             d_d + b0, d_c + b0, st);
+                             d_d + b0, d_c + b0, st, 0, k0);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)next_states + sw * b0, d_ns + sw * b0, sw * nb, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)reward + rw * b0, d_r + rw * b0, rw * nb, cudaMemcpyDeviceToHost, st));
@@ -1342,6 +1364,24 @@ extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *
     }
     for (int h = 0; h < MAPF_HOST_STREAMS; ++h) CUDA_TRY(cudaStreamSynchronize(ctx->hs[h]));
     return MAPF_OK;
+}
+
+extern "C" int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *actions, int64_t B,
+                              const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
+                              uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
+                              uint8_t *collision) {
+    if (B > 0 && !states) return fail(MAPF_ERR_INVALID, "mapf_step_host: bad argument");
+    return step_host_impl(ctx, states, nullptr, actions, B, uniforms, seed, step_index, env_offset, options, next_states,
+                          reward, prob, done, collision);
+}
+
+extern "C" int mapf_step_host_resident(mapf_ctx *ctx, void *states_dev, const int32_t *actions, int64_t B,
+                                       const double *uniforms, uint64_t seed, uint64_t step_index, int64_t env_offset,
+                                       uint32_t options, void *next_states, double *reward, double *prob, uint8_t *done,
+                                       uint8_t *collision) {
+    if (B > 0 && !states_dev) return fail(MAPF_ERR_INVALID, "mapf_step_host_resident: bad argument");
+    return step_host_impl(ctx, nullptr, states_dev, actions, B, uniforms, seed, step_index, env_offset, options, next_states,
+                          reward, prob, done, collision);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,9 @@ struct KernelSet {
     const void *step_philox2 = nullptr;  // ... EPT=2 (128-bit I/O)
     const void *step_tape = nullptr;     // k_step<N, W, LUTS, TAPE=true, EPT=1>
     const void *step_philox1c = nullptr, *step_philox2c = nullptr, *step_tape_c = nullptr;  // ... COMPACT outputs
+    // ... KEEP = true (mapf_step_host_resident: next states also stored to the device-resident array), plain / COMPACT
+    const void *step_philox1k = nullptr, *step_philox2k = nullptr, *step_tape_k = nullptr;
+    const void *step_philox1ck = nullptr, *step_philox2ck = nullptr, *step_tape_ck = nullptr;
     const void *rollout_philox = nullptr, *rollout_tape = nullptr;  // k_rollout<N, W, LUTS, TAPE, EPT=1>
     const void *rollout_philox2 = nullptr;                            // ... EPT=2 (128-bit stores)
     const void *rollout_philox_rnd = nullptr, *rollout_philox2_rnd = nullptr, *rollout_tape_rnd = nullptr;  // actions == NULL

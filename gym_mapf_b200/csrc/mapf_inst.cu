@@ -15,6 +15,12 @@ static void fill(KernelSet *k) {
     k->step_philox1c = (const void *)k_step<N, W, LUTS, false, 1, true>;
     k->step_philox2c = (const void *)k_step<N, W, LUTS, false, 2, true>;
     k->step_tape_c = (const void *)k_step<N, W, LUTS, true, 1, true>;
+    k->step_philox1k = (const void *)k_step<N, W, LUTS, false, 1, false, true>;
+    k->step_philox2k = (const void *)k_step<N, W, LUTS, false, 2, false, true>;
+    k->step_tape_k = (const void *)k_step<N, W, LUTS, true, 1, false, true>;
+    k->step_philox1ck = (const void *)k_step<N, W, LUTS, false, 1, true, true>;
+    k->step_philox2ck = (const void *)k_step<N, W, LUTS, false, 2, true, true>;
+    k->step_tape_ck = (const void *)k_step<N, W, LUTS, true, 1, true, true>;
     k->rollout_philox = (const void *)k_rollout<N, W, LUTS, false, 1, true>;
     k->rollout_philox_rnd = (const void *)k_rollout<N, W, LUTS, false, 1, false>;
     if constexpr (N <= 6) {

@@ -1239,12 +1239,15 @@ __device__ __forceinline__ void load_raw(const u64 *states, const int *__restric
 // iteration ahead by the caller.
 // COMPACT (MAPF_OPT_COMPACT): `reward` receives one code byte per env instead of the double, `done` the flag byte
 // MAPF_FLAG_DONE | MAPF_FLAG_COLLISION, `coll` nothing: 18 instead of 26 result bytes per env.
-template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT>
+// KEEP (mapf_step_host_resident): the next states are stored twice, to `next_states` (the caller's host buffer) and to
+// `keep` (the envs' device-resident states, normally the array they were read from: every thread reads an item's states
+// before it writes them and no other thread touches that item, so in place is safe).
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT, bool KEEP>
 __device__ __forceinline__ void step_item(const DevSpec &sp, const SmemTables &tb, u32 it,
                                           const RawIn<WORDS, EPT> &raw, const u32 (&draws)[EPT][((N + 3) / 4) * 4],
                                           const double *__restrict__ uniforms, u32 opts, u64 *next_states,
                                           double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done,
-                                          u8 *__restrict__ coll) {
+                                          u8 *__restrict__ coll, u64 *keep) {
     constexpr int NW = ((N + 3) / 4) * 4;
     EnvIn<N> in[EPT];
     const u32 b = it * EPT;
@@ -1268,6 +1271,13 @@ __device__ __forceinline__ void step_item(const DevSpec &sp, const SmemTables &t
 #if MAPF_ABLATE == 3  // experiment: almost no stores (the condition is never true, but the compiler cannot know)
     if (o[0].prob < -1.0)
 #endif
+    if (KEEP) {
+        if (EPT == 2 && WORDS == 1) reinterpret_cast<ulonglong2 *>(keep)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
+        else {
+#pragma unroll
+            for (int q = 0; q < EPT; ++q) store_state<WORDS>(keep, b + q, o[q].lo, o[q].hi);
+        }
+    }
     if (EPT == 2) {
         if (WORDS == 1) reinterpret_cast<ulonglong2 *>(next_states)[it] = make_ulonglong2(o[0].lo, o[EPT - 1].lo);
         else {
@@ -1311,11 +1321,12 @@ __device__ __forceinline__ void item_draws(const PhiloxKeys &keys, u64 env0, u64
     }
 }
 
-template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT = false>
+template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT = false, bool KEEP = false>
 __global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
 k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
        const double *__restrict__ uniforms, u64 step, u64 env0, u32 opts, u64 *next_states,
-       double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll) {
+       double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll,
+       u64 *keep) {
     extern __shared__ __align__(16) unsigned char smem[];
     // Programmatic dependent launch: let the next kernel of the stream start its prologue (table staging) while
     // this grid drains, and do our own prologue before waiting for the previous grid's results to be visible.
@@ -1356,8 +1367,8 @@ k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ a
         const RawIn<WORDS, EPT> cur = raw;
         const u32 it_next = it + stride;
         if (it_next < n_items) load_raw<WORDS, EPT>(states, actions, it_next, raw);  // in flight during the compute below
-        step_item<N, WORDS, LUTS, TAPE, EPT, COMPACT>(sp, tb, it, cur, draws, uniforms, opts, next_states, reward, prob, done,
-                                                      coll);
+        step_item<N, WORDS, LUTS, TAPE, EPT, COMPACT, KEEP>(sp, tb, it, cur, draws, uniforms, opts, next_states, reward, prob,
+                                                            done, coll, keep);
 #ifdef MAPF_TRACE
         if (trace_iter == 0) TRACE(4);
         TRACE(8 + trace_iter);

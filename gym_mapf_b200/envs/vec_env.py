@@ -64,70 +64,55 @@ class VecMapfEnv:
         """Every env back on the start state (reference mapf_env.py:290-293).  Returns the state tensor."""
         s0 = self.engine.states_from_ints([self.engine.s0])
         self.states.copy_(s0.expand_as(self.states) if self.engine.words == 1 else s0.expand(self.num_envs, 2))
-        self._where = "device"
         return self.states
 
     def set_states(self, states):
         self.states.copy_(states)
-        self._where = "device"
-
-    # The env states live in ONE place at a time: on the device (step / rollout / reset / set_states) or in the pinned
-    # host mirror (step_host).  Whichever path runs next first pulls the states from where the last step left them, so
-    # device-side and host-side steps can be mixed freely and never continue from stale states.
-    def _states_on_device(self):
-        if getattr(self, "_where", "device") == "host":
-            if self._ring is not None:  # never alias the result set the next step() writes
-                self.states = self.engine.new_states(self.num_envs)
-            self.states.copy_(self._host_states)
-            self._where = "device"
-
-    def _states_on_host(self):
-        if not hasattr(self, "_host_states"):
-            self._host_states = self._torch.empty(self.states.shape, dtype=self._torch.int64).pin_memory()
-            self._where = "device"
-        if getattr(self, "_where", "device") == "device":
-            self._host_states.copy_(self.states)
-            self._where = "host"
 
     # ---- sampled transitions -----------------------------------------------------------------------------------
     def step(self, actions, uniforms=None):
         """One joint step of every env.  Returns (next_states, rewards, dones, info) with
         info = {"prob": f64[B], "collision": bool[B]}.  `uniforms` (f64[B, n]) replays given draws bit-exactly;
         without it the device-side Philox stream keyed by (seed, env, step) is used."""
-        self._states_on_device()
         out = None if self._ring is None else self._ring[self.step_count & 1]
+        if out is not None and out[0].data_ptr() == self.states.data_ptr():  # after an odd number of step_host() calls
+            out = self._ring[(self.step_count + 1) & 1]
         ns, reward, prob, done, coll = self.engine.step(
             self.states, actions, uniforms=uniforms, seed=self.seed, step_index=self.step_count,
             env_offset=self.env_offset, auto_reset=self.auto_reset, out=out)
         self.states = ns
+        self._states_shared = True  # the caller holds this tensor: step_host() must not advance it in place
         self.step_count += 1
         return ns, reward, done, {"prob": prob, "collision": coll}
 
     def rollout(self, T, actions=None, uniforms=None):
         """T steps in one launch.  `actions`: int32[T, B] or None for a uniformly random policy.  Returns a Rollout
         of step-major [T, B] tensors; the env states advance by T steps."""
-        self._states_on_device()
         out = self.engine.rollout(self.states, actions, T, uniforms=uniforms, seed=self.seed,
                                   step_index=self.step_count, env_offset=self.env_offset, auto_reset=self.auto_reset)
         self.step_count += T
         return Rollout(*out)
 
     def step_host(self, actions, out=None, uniforms=None):
-        """End-to-end host path: `actions` is a CPU int32 array/tensor; the env states are read from and written
-        back to a host mirror, and the five results land in host memory (numpy arrays, or `out`)."""
+        """End-to-end host path, the batched `MapfEnv.step(action)` (reference mapf_env.py:237-266): `actions` is a CPU
+        int32 array/tensor; the env states stay on the device, where `step` / `rollout` / `reset` / `set_states` keep
+        them too (the reference keeps `self.s` in the env), so device-side and host-side steps can be mixed freely; the
+        five results land in host memory (pinned tensors, or `out`)."""
         B = self.num_envs
-        self._states_on_host()
         if out is None:
             out = (self._torch.empty(self.states.shape, dtype=self._torch.int64).pin_memory(),
                    self._torch.empty(B, dtype=self._torch.float64).pin_memory(),
                    self._torch.empty(B, dtype=self._torch.float64).pin_memory(),
                    self._torch.empty(B, dtype=self._torch.bool).pin_memory(),
                    self._torch.empty(B, dtype=self._torch.bool).pin_memory())
-        self.engine.step_host(self._host_states, actions, out, uniforms=uniforms, seed=self.seed,
-                              step_index=self.step_count, env_offset=self.env_offset, auto_reset=self.auto_reset)
-        self._host_states, out = out[0], (self._host_states,) + tuple(out[1:])
+        if getattr(self, "_states_shared", False):
+            self.states = self.states.clone()
+            self._states_shared = False
+        self.engine.step_host_resident(self.states, actions, out, uniforms=uniforms, seed=self.seed,
+                                       step_index=self.step_count, env_offset=self.env_offset,
+                                       auto_reset=self.auto_reset)
         self.step_count += 1
-        return (self._host_states,) + tuple(out[1:])
+        return tuple(out)
 
     # ---- transition table --------------------------------------------------------------------------------------
     def transitions(self, states, actions):
@@ -277,5 +262,6 @@ class MultiMapVecEnv:
             part.step(self.states[lo:hi], actions[lo:hi], uniforms=uniforms, seed=self.seed, step_index=self.step_count,
                       env_offset=self.env_offset + lo, auto_reset=self.auto_reset, out=out)
         self.states = ns
+        self._states_shared = True  # the caller holds this tensor: step_host() must not advance it in place
         self.step_count += 1
         return ns, reward, done, {"prob": prob, "collision": coll}

@@ -187,6 +187,18 @@ int mapf_step_host(mapf_ctx *ctx, const void *states, const int32_t *actions, in
                    uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
                    double *reward, double *prob, uint8_t *done, uint8_t *collision);
 
+/* mapf_step_host for envs whose states are RESIDENT on the device, as the reference's are in the env object: MapfEnv.step
+ * receives only the action and keeps self.s itself (mapf_env.py:237, 264).  states_dev is DEVICE memory of the context's GPU
+ * holding the B current states; it is read and overwritten in place with the next states (under MAPF_OPT_AUTO_RESET the
+ * start state for an env that was done), which are also written to the host buffer next_states, like the other four
+ * results.  Only the actions cross the host link on the way in: 4 instead of 4 + 8 * words bytes per env.  All other
+ * arguments, options and results are those of mapf_step_host and the results are bit-identical to it.  The call runs on the
+ * context's own streams: work that produced states_dev must have completed before it is made; it returns when the results
+ * are in host memory and states_dev is updated. */
+int mapf_step_host_resident(mapf_ctx *ctx, void *states_dev, const int32_t *actions, int64_t B, const double *uniforms,
+                            uint64_t seed, uint64_t step_index, int64_t env_offset, uint32_t options, void *next_states,
+                            double *reward, double *prob, uint8_t *done, uint8_t *collision);
+
 /* ---- rows next to the hot path ------------------------------------------------------------------ */
 
 /* The consumer loop of a planner over the table, without materialising it:

@@ -224,6 +224,75 @@ def test_compact_result_layout(torch):
                     assert torch.equal(a, b.cpu()), pinned
 
 
+def test_step_host_resident_matches_the_oracle_and_step_host(torch):
+    """mapf_step_host_resident (states stay on the device, only the actions come from the host): replayed uniforms equal
+    the C oracle, Philox draws equal mapf_step_host, and the device-resident states end up equal to the returned next
+    states -- one- and two-word states; pinned (zero-copy launch), pageable (staged copies) and small (pinned scratch)
+    batches; even (128-bit kernel) and odd (scalar kernel) sizes; default and compact result layouts; two chained steps."""
+    for name, scen, n, soc in (("room-32-32-4", 1, 4, True), ("room-64-64-8", 1, 8, False)):
+        env = _env(name, scen, n, soc)
+        eng, ora = env.engine, _oracle(env, soc)
+        for B in (70000, 70001, 600):
+            rng = np.random.default_rng(B)
+            cells = rng.integers(0, min(eng.L, 60), (B, eng.n)).astype(np.int32)  # dense: clashes and terminal states
+            lo, hi = ora.encode(cells)
+            st0 = eng.encode(torch.from_numpy(cells).cuda())
+            st0[: B // 3] = eng.states_from_ints([eng.s0] * (B // 3))
+            h0 = st0.cpu().numpy().view(np.uint64)
+            lo, hi = (h0, np.zeros_like(h0)) if eng.words == 1 else (h0[:, 0].copy(), h0[:, 1].copy())
+            acts = rng.integers(0, eng.nA, (2, B)).astype(np.int32)
+            unis = rng.random((2, B, eng.n))
+            for pinned in (True, False):
+                mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+
+                def outs(compact=False):
+                    if compact:
+                        return (mk(torch.empty(eng.state_shape(B), dtype=torch.int64)), mk(torch.empty(B, dtype=torch.uint8)),
+                                mk(torch.empty(B, dtype=torch.float64)), mk(torch.empty(B, dtype=torch.uint8)))
+                    return (mk(torch.empty(eng.state_shape(B), dtype=torch.int64)), mk(torch.empty(B, dtype=torch.float64)),
+                            mk(torch.empty(B, dtype=torch.float64)), mk(torch.empty(B, dtype=torch.bool)),
+                            mk(torch.empty(B, dtype=torch.bool)))
+                # replayed uniforms, reference semantics (no auto-reset), two chained steps vs the oracle
+                dev = st0.clone()
+                clo, chi = lo, hi
+                for t in range(2):
+                    out = outs()
+                    eng.step_host_resident(dev, mk(torch.from_numpy(acts[t])), out, uniforms=mk(torch.from_numpy(unis[t])))
+                    want = ora.step(clo, chi, acts[t].astype(np.int64), unis[t])
+                    ns = out[0].numpy().view(np.uint64)
+                    glo, ghi = (ns, np.zeros_like(ns)) if eng.words == 1 else (ns[:, 0], ns[:, 1])
+                    assert np.array_equal(glo, want["next_lo"]) and np.array_equal(ghi, want["next_hi"]), (name, B, pinned, t)
+                    assert np.array_equal(out[1].numpy().view(np.uint64), want["reward"].view(np.uint64))
+                    assert np.array_equal(out[2].numpy().view(np.uint64), want["prob"].view(np.uint64))
+                    assert np.array_equal(out[3].numpy().astype(np.uint8), want["done"])
+                    assert np.array_equal(out[4].numpy().astype(np.uint8), want["collision"])
+                    assert torch.equal(dev.cpu(), out[0]), "resident states == returned next states"
+                    clo, chi = want["next_lo"], want["next_hi"]
+                    if t == 0:
+                        assert int(want["collision"].sum()) > 0 and int(want["done"].sum()) > int(want["collision"].sum())
+                # device Philox draws with auto-reset: resident == stateless host step, default and compact layouts
+                for compact in (False, True):
+                    dev = st0.clone()
+                    host = mk(st0.cpu())
+                    for t in range(2):
+                        a = mk(torch.from_numpy(acts[t]))
+                        got, want = outs(compact), outs(compact)
+                        eng.step_host_resident(dev, a, got, seed=77, step_index=t, env_offset=5, auto_reset=True, compact=compact)
+                        eng.step_host(host, a, want, seed=77, step_index=t, env_offset=5, auto_reset=True, compact=compact)
+                        for x, y in zip(got, want):
+                            assert torch.equal(x, y), (name, B, pinned, compact, t)
+                        assert torch.equal(dev.cpu(), got[0])
+                        host = want[0]
+    # the resident states must be device memory of the context's GPU
+    from gym_mapf_b200 import _native
+    bad = torch.zeros(eng.state_shape(600), dtype=torch.int64).pin_memory()
+    with pytest.raises(ValueError):
+        eng.step_host_resident(bad, torch.from_numpy(acts[0]), outs())
+    rc = _native.lib().mapf_step_host_resident(eng._h, bad.data_ptr(), acts[0].ctypes.data, 600, None, 0, 0, 0, 0,
+                                               *(t.data_ptr() for t in outs()))
+    assert rc == _native.MAPF_ERR_INVALID
+
+
 def test_share_sm_and_pools_give_identical_results(torch):
     """MAPF_OPT_SHARE_SM only changes the launch shape; two pools stepped on two streams reproduce the single launch."""
     env = _env("room-32-32-4", 1, 4)
