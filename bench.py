@@ -580,8 +580,26 @@ def run_ours(args):
                       "actions from and all five results to pinned host buffers)",
                "host_numa_bind": prev_affinity is not None,
                "host_link_gbs": world * B * 30 * n_e2e / dt / 1e9}
-        if rank == 0:  # the resident states ARE the returned next states
-            assert torch.equal(ds.cpu(), hout[0]), "mapf_step_host_resident: device states differ from the returned ones"
+        resident_ok = bool(torch.equal(ds.cpu(), hout[0]))  # the resident states ARE the returned next states
+        # sample of the same call for the oracle check below: 2**16 envs from known dense states (outside the timed region)
+        e2e_payload = None
+        if rank == 0 and not args.no_cpu:
+            me = 1 << 16
+            gs = torch.Generator(device=dev)
+            gs.manual_seed(11)  # agents packed into 40 cells: terminal states, clashes and goals all occur in the sample
+            ds_s = eng.encode(torch.randint(0, 40, (me, N_AGENTS), generator=gs, device=dev, dtype=torch.int32))
+            s_before = ds_s.cpu().numpy().view(np.uint64).copy()
+            ha_s = ha[:me].clone().pin_memory()
+            out_s = tuple(t[:me].clone().pin_memory() for t in hout)
+            eng.step_host_resident(ds_s, ha_s, out_s, seed=seed, step_index=7, env_offset=env_offset, auto_reset=True)
+            resident_ok = resident_ok and bool(torch.equal(ds_s.cpu(), out_s[0]))
+            e2e_payload = {"kind": "step", "spec": None, "s_lo": s_before,
+                           "s_hi": np.zeros(me, np.uint64), "action": ha_s.numpy().astype(np.int64), "seed": seed,
+                           "step_index": 7, "env_offset": env_offset, "auto_reset": True, "s0": int(eng.s0),
+                           "next_lo": out_s[0].numpy().view(np.uint64).copy(), "next_hi": np.zeros(me, np.uint64),
+                           "reward": out_s[1].numpy().copy(), "prob": out_s[2].numpy().copy(),
+                           "done": out_s[3].numpy().astype(np.uint8), "collision": out_s[4].numpy().astype(np.uint8)}
+        e2e["resident_states_match"] = resident_ok
         # the stateless call (round-1 headline): the states cross the link too, 12 B/env in
         dts = host_leg(lambda i: eng.step_host(hs, ha, hout, seed=seed, step_index=i, env_offset=env_offset, auto_reset=True))
         e2e["stateless"] = {"value": world * B * n_e2e / dts, "unit": "transitions/s", "h2d_bytes_per_step": B * 12 * world,
@@ -664,6 +682,11 @@ def run_ours(args):
             ok, what = verify_payload(head_payload)
             line["parity"] = ok
             line["parity_sample"] = "last timed launch of the bench kernel: " + what
+            if e2e is not None and e2e_payload is not None:
+                e2e_payload["spec"] = head_payload["spec"]
+                ok, what = verify_payload(e2e_payload)
+                e2e["parity"] = bool(ok and e2e["resident_states_match"])
+                e2e["parity_sample"] = "one mapf_step_host_resident call outside the timed region: " + what
             block = {}
             for name, entry, payload in others:
                 ok, what = verify_payload(payload)

@@ -371,6 +371,11 @@ def run_all(device_index, world, rank, only=None, quick=False):
     add("c1", lambda: c1_case(dev, peak, device_index))
     add("c2_expand", lambda: expand_case("C2 expand: room-32-32-4 scen 1, 4 agents, SoC; random (s, a) rows",
                                          make("room-32-32-4", 1, 4, True, device_index), True, dev, peak, target, 2))
+    add("c3_rows", lambda: expand_case(
+        "C3 rows sampled over the WHOLE table: maze-32-32-4 scen 10, 6 agents, Makespan; uniformly random (s, a) rows "
+        "(c3_table is one slab of consecutive states next to the scenario's start state, where a fifth of the records are "
+        "collisions; this is what an average slab of the full table costs)",
+        make("maze-32-32-4", 10, 6, False, device_index), False, dev, peak, target, 3))
     add("c2_rollout", lambda: rollout_case("C2 rollout: room-32-32-4 scen 1, 4 agents, SoC; 32 steps per launch, actions given",
                                            make("room-32-32-4", 1, 4, True, device_index), True, dev, peak,
                                            (1 << 18) if quick else (1 << 20), 32))
