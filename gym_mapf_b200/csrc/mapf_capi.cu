@@ -66,6 +66,7 @@ struct mapf_ctx {
     size_t smem_base = 0;        // small tables + staged move table
     size_t smem_expand = 0;      // smem_base + per-warp expand slabs
     size_t smem_backup = 0;      // smem_base + per-warp backup slabs
+    int threads_step = 0;  // CTA size of k_step (ks.step_threads, else `threads`)
     int grid_step1 = 0, grid_step2 = 0, grid_step_tape = 0, grid_rollout = 0, grid_rollout2 = 0, grid_rollout_tape = 0;
     int grid_lanes = 0, grid_lanes_tape = 0;
     LaneConsts lanes;                   // per-lane constants of the lane-per-agent step (k_step_lanes)
@@ -595,6 +596,7 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
 #ifdef MAPF_BITMAP_ENTRIES
     ctx->smem_base += bm_blob;
 #endif
+    ctx->threads_step = ctx->ks.step_threads ? ctx->ks.step_threads : ctx->threads;
     ctx->threads_expand = ctx->ks.expand_threads ? ctx->ks.expand_threads : ctx->threads;
     if (ctx->smem_base + (size_t)(ctx->threads_expand / 32) * ctx->ks.expand_slab_bytes > smem_limit)
         ctx->threads_expand = ctx->threads;  // the wide CTA's slabs do not fit next to this map's table
@@ -602,18 +604,18 @@ extern "C" int mapf_ctx_create(const mapf_spec *spec, int device, mapf_ctx **out
     ctx->smem_backup = ctx->smem_base + (size_t)(ctx->threads / 32) * ctx->ks.backup_slab_bytes;
     int grid_keep = 0;  // the KEEP kernels are launched with their plain twins' grids (host-link-bound callers)
     struct { const void *fn; size_t smem; int *grid; int threads; } plan[] = {
-        {ctx->ks.step_philox1k, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_philox2k, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_tape_k, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_philox1ck, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_philox2ck, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_tape_ck, ctx->smem_base, &grid_keep},
-        {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1},
-        {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2},
-        {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape},
-        {ctx->ks.step_philox1c, ctx->smem_base, &ctx->grid_step1},
-        {ctx->ks.step_philox2c, ctx->smem_base, &ctx->grid_step2},
-        {ctx->ks.step_tape_c, ctx->smem_base, &ctx->grid_step_tape},
+        {ctx->ks.step_philox1k, ctx->smem_base, &grid_keep, ctx->threads_step},
+        {ctx->ks.step_philox2k, ctx->smem_base, &grid_keep, ctx->ks.step_wide_ept2 ? ctx->threads_step : 0},
+        {ctx->ks.step_tape_k, ctx->smem_base, &grid_keep, ctx->threads_step},
+        {ctx->ks.step_philox1ck, ctx->smem_base, &grid_keep, ctx->threads_step},
+        {ctx->ks.step_philox2ck, ctx->smem_base, &grid_keep, ctx->ks.step_wide_ept2 ? ctx->threads_step : 0},
+        {ctx->ks.step_tape_ck, ctx->smem_base, &grid_keep, ctx->threads_step},
+        {ctx->ks.step_philox1, ctx->smem_base, &ctx->grid_step1, ctx->threads_step},
+        {ctx->ks.step_philox2, ctx->smem_base, &ctx->grid_step2, ctx->ks.step_wide_ept2 ? ctx->threads_step : 0},
+        {ctx->ks.step_tape, ctx->smem_base, &ctx->grid_step_tape, ctx->threads_step},
+        {ctx->ks.step_philox1c, ctx->smem_base, &ctx->grid_step1, ctx->threads_step},
+        {ctx->ks.step_philox2c, ctx->smem_base, &ctx->grid_step2, ctx->ks.step_wide_ept2 ? ctx->threads_step : 0},
+        {ctx->ks.step_tape_c, ctx->smem_base, &ctx->grid_step_tape, ctx->threads_step},
         {ctx->ks.rollout_philox, ctx->smem_base, &ctx->grid_rollout},
         {ctx->ks.rollout_philox2, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
         {ctx->ks.rollout_philox2_rnd, ctx->smem_base, &ctx->grid_rollout2, MAPF_ROLLOUT2_THREADS},
@@ -1093,17 +1095,21 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
         const void *fn;
         int grid;
         const KernelSet &ks = ctx->ks;
+        int threads = ctx->threads;
         if (uniforms) {
             fn = keep ? (compact ? ks.step_tape_ck : ks.step_tape_k) : (compact ? ks.step_tape_c : ks.step_tape);
-            grid = grid_for(nb, ctx->threads, ctx->grid_step_tape);
-        } else if (force_ept != 1 && (nb & 1) == 0 && aligned(a_states, 16) && aligned(a_ns, 16) && aligned(a_actions, 8) &&
+            threads = ctx->threads_step;
+            grid = grid_for(nb, threads, ctx->grid_step_tape);
+        } else if (force_ept != 1 && (!ks.step_threads || ks.step_wide_ept2) && (nb & 1) == 0 && aligned(a_states, 16) && aligned(a_ns, 16) && aligned(a_actions, 8) &&
                    aligned(a_r, compact ? 2 : 16) && aligned(a_p, 16) && aligned(a_d, 2) && (compact || aligned(a_c, 2)) &&
                    aligned(a_keep, 16)) {
             fn = keep ? (compact ? ks.step_philox2ck : ks.step_philox2k) : (compact ? ks.step_philox2c : ks.step_philox2);
-            grid = grid_for(nb / 2, ctx->threads, ctx->grid_step2);
+            if (ks.step_wide_ept2) threads = ctx->threads_step;
+            grid = grid_for(nb / 2, threads, ctx->grid_step2);
         } else {
             fn = keep ? (compact ? ks.step_philox1ck : ks.step_philox1k) : (compact ? ks.step_philox1c : ks.step_philox1);
-            grid = grid_for(nb, ctx->threads, ctx->grid_step1);
+            threads = ctx->threads_step;
+            grid = grid_for(nb, threads, ctx->grid_step1);
         }
         if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;
         if ((options & MAPF_OPT_SHARE_SM) && grid > ctx->info.sm_count) grid = ctx->info.sm_count;
@@ -1121,7 +1127,7 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             // previous kernel of the stream is still draining
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid);
-            cfg.blockDim = dim3(ctx->threads);
+            cfg.blockDim = dim3(threads);
             cfg.dynamicSmemBytes = ctx->smem_base;
             cfg.stream = stream;
             cudaLaunchAttribute attr[1];
@@ -1132,7 +1138,7 @@ static int launch_step(const mapf_ctx *ctx, const void *states, const int32_t *a
             cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
             if (e != cudaSuccess) return fail(MAPF_ERR_CUDA, "launch k_step: %s", cudaGetErrorString(e));
         } else {
-            LAUNCH(fn, grid, ctx->threads, ctx->smem_base, stream, args);
+            LAUNCH(fn, grid, threads, ctx->smem_base, stream, args);
         }
     }
     return MAPF_OK;

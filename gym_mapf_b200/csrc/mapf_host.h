@@ -26,6 +26,8 @@ struct KernelSet {
     const void *pred_count = nullptr, *pred_emit = nullptr, *project = nullptr;
     size_t expand_slab_bytes = 0;        // per warp
     int expand_threads = 0;              // CTA size of k_expand (0: the context's)
+    int step_wide_ept2 = 0;              // experiment builds: the wide CTAs also run the EPT = 2 kernels
+    int step_threads = 0;                // CTA size of the EPT = 1 k_step kernels, which are then always used (0: the context's)
     size_t backup_slab_bytes = 0;        // per warp
 };
 

@@ -64,6 +64,8 @@ static void fill(KernelSet *k) {
     k->project = (const void *)k_project<N, W>;
     k->expand_slab_bytes = sizeof(ExpandSlab<N>);
     k->expand_threads = LUTS ? EXPAND_THREADS(N) : 0;  // 0: the context's CTA size
+    k->step_wide_ept2 = STEP_WIDE_EPT2;
+    k->step_threads = LUTS && N >= STEP_WIDE_MIN_AGENTS ? STEP_WIDE_THREADS : 0;  // != 0: one env per thread, wide CTAs
     k->backup_slab_bytes = sizeof(BackupSlab<N>);
 }
 

@@ -1321,8 +1321,23 @@ __device__ __forceinline__ void item_draws(const PhiloxKeys &keys, u64 env0, u64
     }
 }
 
+// From STEP_WIDE_MIN_AGENTS agents on (one CTA per SM: two envs per thread want ~128 registers, which leaves 16 warps
+// per SM) the step kernel runs ONE env per thread in CTAs of STEP_WIDE_THREADS threads: <= 80 registers, 24 warps per SM.
+// The EPT = 2 instantiations of those agent counts are not launched (mapf_capi.cu: launch_step).  Measured against the
+// 512-thread EPT = 2 launch (profiles/r02_ablations.txt): 7 agents +1.4 / +3.0 %, 8 agents (C4) +2.8 %, 9 agents +2.3 /
+// +8.6 %, 10 agents +8.9 %; 640 or 1024 threads and two envs per thread in 768-thread CTAs (a spill) are slower.
+#ifndef STEP_WIDE_MIN_AGENTS
+#define STEP_WIDE_MIN_AGENTS 7
+#endif
+#ifndef STEP_WIDE_THREADS
+#define STEP_WIDE_THREADS 768
+#endif
+#ifndef STEP_WIDE_EPT2
+#define STEP_WIDE_EPT2 0  // experiment: the wide CTAs keep two envs per thread (80 registers: a small spill)
+#endif
+#define STEP_THREADS(N, EPT) ((N) >= STEP_WIDE_MIN_AGENTS && ((EPT) == 1 || STEP_WIDE_EPT2) ? STEP_WIDE_THREADS : MAPF_MAX_THREADS)
 template <int N, int WORDS, bool LUTS, bool TAPE, int EPT, bool COMPACT = false, bool KEEP = false>
-__global__ void __launch_bounds__(MAPF_MAX_THREADS, MAPF_MIN_BLOCKS(N))
+__global__ void __launch_bounds__(STEP_THREADS(N, EPT), MAPF_MIN_BLOCKS(N))
 k_step(DevSpec sp, PhiloxKeys keys, const u64 *states, const int *__restrict__ actions, u32 B,
        const double *__restrict__ uniforms, u64 step, u64 env0, u32 opts, u64 *next_states,
        double *__restrict__ reward, double *__restrict__ prob, u8 *__restrict__ done, u8 *__restrict__ coll,
