@@ -207,7 +207,7 @@ typedef struct { uint64_t v[8]; } checks; /* count, n_coll, n_done, sum_lo, sum_
 /* mapf_env.py:448-479 -- one row.  When `next_lo` is NULL only the checksums are accumulated. */
 static int64_t emit_row(const oracle_env *e, u128 s, int64_t a, int64_t base, uint64_t *next_lo, uint64_t *next_hi,
                         double *prob, double *reward, uint8_t *done, uint8_t *coll, checks *cs) {
-    int32_t prev[MAX_AGENTS], nxt[MAX_AGENTS];
+    int32_t prev[MAX_AGENTS] = {0}, nxt[MAX_AGENTS];
     int acts[MAX_AGENTS], digit[MAX_AGENTS];
     const agent_moves *mv[MAX_AGENTS];
     decode_state(e, s, prev);
